@@ -1,0 +1,245 @@
+/*
+ * mirror_maze_cuda.h — C-ABI drop-in boundary for mirror-maze's per-pixel render kernel on B200 (sm_100a).
+ *
+ * What this replaces.  The reference has no plugin/operator API: the boundary of its hot path is the Metal
+ * argument table of `compute_shader` (reference src/shaders.metal:245-259) as bound by the frame loop
+ * (reference src/main.rs:867-886): texture(0) = screen, texture(1) = noise, buffer(0) = chunk list,
+ * buffer(1) = rects, buffer(2) = BVH nodes, buffer(3) = prim indices, buffer(4) = one `uni` by value,
+ * buffer(5) = materials, buffer(6) = emissions, plus the grid shape (src/main.rs:641-650).
+ * Every entry point below names the reference call it stands in for.  Plain pointers and sizes only.
+ *
+ * A Rust driver binds this header with an `extern "C"` block; all POD structs are
+ * byte-identical to the reference's #[repr(C)] types (src/main.rs:32-90, src/maths.rs:3-16,50-52).
+ *
+ * Threading: a context is not thread-safe; it owns one CUDA device, one stream and all device memory.
+ * Errors: every function returns 0 on success or a negative MM_ERR_* code and never aborts or throws
+ * across the ABI (the reference panics through .expect()/.unwrap(), e.g. src/utils.rs:19,43).
+ */
+#ifndef MIRROR_MAZE_CUDA_H
+#define MIRROR_MAZE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- POD layouts ------------------------------------------------------------- */
+
+typedef struct mm_float2 { float x, y; } mm_float2;             /* maths.rs:50-52  (8 B)  */
+typedef struct mm_float3 { float x, y, z; } mm_float3;          /* maths.rs:14-16  (12 B) */
+typedef struct mm_float4 { float x, y, z, w; } mm_float4;       /* maths.rs:3-5    (16 B) */
+
+/* main.rs:51-58 `Plane`  ==  shaders.metal:19-24 `rect`  (48 B, align 4) */
+typedef struct mm_plane { mm_float3 origin, v, u, color; } mm_plane;
+
+/* main.rs:74-81 `BVHNode`  ==  shaders.metal:30-35 `bvh_node`  (32 B).
+ * tri_count > 0: leaf over indices[left_first .. left_first+tri_count); else children at left_first, +1. */
+typedef struct mm_bvh_node { mm_float3 aabb_min, aabb_max; uint32_t left_first, tri_count; } mm_bvh_node;
+
+/* main.rs:32-39 `Camera`  ==  shaders.metal:37-42 `camera`  (40 B) */
+typedef struct mm_camera { mm_float3 camera_center; float focal_length; mm_float4 rotation; mm_float2 viewport; } mm_camera;
+
+/* main.rs:41-49 `Uniform`  ==  shaders.metal:237-243 `uni`  (56 B) */
+typedef struct mm_uniform { mm_camera cam; float view_width, view_height; uint32_t chunk_width, time; } mm_uniform;
+
+/* One entry of `pixel_update_buffer` (shaders.metal:248; main.rs:293-326): top-left pixel of a chunk. */
+typedef struct mm_chunk { uint32_t x, y; } mm_chunk;
+
+/* ---- Dispatch parameters ------------------------------------------------------------------------- */
+
+/*
+ * The reference hard-codes these in the shader or the dispatch (shaders.metal:294-295 bounce_limit = 5,
+ * mirror_limit = 15; main.rs:641-650 grid 32x24 groups of 32x32 threads => spp = 1024/16 = 64).
+ * They are passed beside the 56-byte `uni` so that its layout stays the reference's.
+ *
+ * Virtual dispatch.  The kernel's RNG seed is a function of the Metal thread coordinates
+ * (shaders.metal:298), so the Metal grid is part of the contract and is kept as a *virtual* grid:
+ *   threads per group T = chunk_width^2 * spp,   dims = (min(32,T), T/min(32,T))   (execution width 32),
+ *   grid = grid_x x grid_y groups,   group (tgid.x, tgid.y) renders chunk  chunks[tgid.x + tgid.y*grid_x]
+ *   (shaders.metal:266 uses (width/2)/ppc as the row stride, which equals grid_x = 32 in the reference's
+ *   only configuration; the stride is grid_x here),  flat = gid.x + dims.x*gid.y,  pixel = flat / spp,
+ *   sample = flat % spp,  texid = tgid*dims + gid.
+ * With spp = 64, chunk 4, grid 32x24 this is the reference dispatch exactly.
+ *
+ * Tiles.  One call renders the groups  g = group_first + k*group_step,  k in [0, group_count)  of the
+ * linear group index g = tgid.x + tgid.y*grid_x.  Seeds depend on g, not on k, so any partition of the
+ * groups over calls or GPUs gives the bits of a single full-grid call.  group_count = 0 means "all".
+ */
+typedef struct mm_params {
+    uint32_t spp;            /* samples per pixel: power of two, 1..256                              */
+    uint32_t bounce_limit;   /* shaders.metal:294                                                    */
+    uint32_t mirror_limit;   /* shaders.metal:295                                                    */
+    uint32_t grid_x, grid_y; /* virtual threadgroups per grid (main.rs:646-650)                      */
+    uint32_t group_first, group_step, group_count;
+    uint32_t flags;          /* MM_FLAG_*                                                            */
+} mm_params;
+
+#define MM_FLAG_COUNTERS      1u   /* fill mm_counters beyond `rays` (slower kernel variant)          */
+#define MM_FLAG_FORCE_LITERAL 2u   /* use the literal-divide traversal for every ray (validation)     */
+#define MM_FLAG_FORCE_GLOBAL  4u   /* keep BVH nodes in global memory even if they fit in shared      */
+
+/* Exact event counts of one render call; identical on CPU oracle and GPU (SURVEY §8 d). */
+typedef struct mm_counters {
+    uint64_t paths;          /* (pixel, sample) pairs traced                                         */
+    uint64_t rays;           /* calls of the traversal routine = bounce-loop iterations (the metric) */
+    uint64_t inner_visits;   /* interior nodes whose two children were slab-tested                   */
+    uint64_t leaf_visits;    /* leaves whose rects were tested                                       */
+    uint64_t rect_tests;     /* ray_rect_intersect calls                                             */
+    uint64_t hits;           /* traversal calls that returned a hit                                  */
+    uint64_t literal_rays;   /* rays traced by the literal-divide traversal (GPU only; 0 on CPU)     */
+    uint64_t max_stack;      /* deepest traversal-stack occupancy seen                               */
+} mm_counters;
+
+/*
+ * Optional per-path observables (definitions: SURVEY Appendix C tail).  Each non-null pointer receives
+ * group_count*T entries, entry [k*T + flat].  Host pointers for mm_render, ignored by the device variants.
+ */
+typedef struct mm_debug {
+    uint32_t *first_hit;     /* beam.index after the n = 0 traversal, 0xFFFFFFFF on miss             */
+    uint32_t *segments;      /* traversal calls made by this path                                    */
+    uint32_t *mirror_hits;   /* final mirror_hits (shaders.metal:305,325)                            */
+    float    *radiance;      /* 3 floats per path: incoming_light before the sqrt tone-map           */
+} mm_debug;
+
+/* ---- Error codes ---------------------------------------------------------------------------------- */
+
+#define MM_OK                 0
+#define MM_ERR_INVALID       -1   /* null pointer, zero size, bad parameter combination              */
+#define MM_ERR_CUDA          -2   /* a CUDA runtime call failed; see mm_last_error                   */
+#define MM_ERR_NO_SCENE      -3   /* render before mm_upload_scene                                   */
+#define MM_ERR_BVH           -4   /* malformed BVH: child out of range, cycle, depth above MM_MAX_STACK */
+#define MM_ERR_UNSUPPORTED   -5   /* spp not a power of two <= 256, chunk_width^2*spp > limits, ...  */
+#define MM_ERR_NOMEM         -6
+
+#define MM_MAX_STACK 48           /* traversal stack entries on the device (reference: 50, unchecked,
+                                     shaders.metal:123); BVH depth is validated against it at upload  */
+
+typedef struct mm_ctx mm_ctx;
+
+/* ---- Context --------------------------------------------------------------------------------------- */
+
+/* Replaces Device::system_default + new_command_queue + pipeline creation (main.rs:616-644). */
+int mm_create(int cuda_device, mm_ctx **out);
+int mm_destroy(mm_ctx *ctx);
+/* Never null; empty string when the last call on ctx succeeded.  mm_last_error(NULL) = last create error. */
+const char *mm_last_error(const mm_ctx *ctx);
+
+/*
+ * Replaces the six make_buf calls and the noise-texture upload (main.rs:667-695, 723-730; utils.rs:86-94).
+ * Copies everything; the caller keeps ownership.  materials: 1 byte per plane (Rust bool).
+ * noise_rgba8: nw*nh*4 bytes, row pitch 4*nw (main.rs:695).  Validates the BVH (MM_ERR_BVH).
+ */
+int mm_upload_scene(mm_ctx *ctx,
+                    const mm_plane *planes, uint32_t n_planes,
+                    const mm_bvh_node *nodes, uint32_t n_nodes,
+                    const uint32_t *indices,
+                    const uint8_t *materials,
+                    const mm_float4 *emissions,
+                    const uint8_t *noise_rgba8, uint32_t noise_w, uint32_t noise_h);
+
+/*
+ * Replaces copy_to_buf(pixel_data) + set_bytes(uni) + dispatch_thread_groups (main.rs:784, 867-886) and the
+ * read-back of the screen texture.  Synchronous.  `chunks` has grid_x*grid_y entries.  The context owns a
+ * persistent device screen image, the counterpart of the reference's GPU-private screen texture
+ * (main.rs:702-709): created zero-filled at first use (and again when the view size changes), written only
+ * at the pixels of the chunks a call renders, kept across calls.  out_rgba is a HOST buffer of
+ * view_height*view_width*4 floats, row-major [y][x][rgba], that receives a copy of the whole screen image
+ * after the kernel.  counters/debug may be null.
+ */
+int mm_render(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params,
+              const mm_chunk *chunks, uint32_t n_chunks,
+              float *out_rgba, mm_counters *counters, const mm_debug *debug);
+
+/*
+ * Device-resident variants for callers that keep frames on the GPU (multi-GPU tile gather, frame batching).
+ * mm_set_chunks replaces copy_to_buf (utils.rs:96-102) and is only needed when the chunk list changes.
+ * mm_render_device is asynchronous on the context's stream (the reference's commit() does not wait either,
+ * main.rs:894); mm_sync waits.  d_image: device pointer, H*W*4 floats.  d_tiles: device pointer,
+ * group_count * chunk_width^2 * 4 floats, tile k = group group_first + k*group_step, pixel order = the
+ * kernel's pixel_number (x offset = pn / chunk, y offset = pn % chunk; shaders.metal:272-275).
+ * Exactly one of d_image / d_tiles may be null.
+ */
+int mm_set_chunks(mm_ctx *ctx, const mm_chunk *chunks, uint32_t n_chunks);
+int mm_render_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params,
+                     float *d_image, float *d_tiles);
+/* Scatter gathered tiles (any rank's d_tiles layout) into an image: tile k -> chunk of group
+ * group_first + k*group_step.  Asynchronous on the context's stream. */
+int mm_scatter_tiles_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params,
+                            const float *d_tiles, float *d_image);
+int mm_sync(mm_ctx *ctx);
+/* Run the context's work on a caller-owned cudaStream_t (e.g. torch's current stream) from now on; NULL
+ * restores the context's own stream.  The caller keeps the stream alive while the context uses it. */
+int mm_set_stream(mm_ctx *ctx, void *stream);
+/* Counters of the most recent mm_render_device (valid after mm_sync). */
+int mm_last_counters(mm_ctx *ctx, mm_counters *out);
+/* Device time of the most recent render kernel in milliseconds (CUDA events on the context's stream). */
+int mm_last_ms(mm_ctx *ctx, float *ms);
+/* The context's cudaStream_t, for callers that order their own work (NCCL, torch) after the kernel. */
+int mm_stream(mm_ctx *ctx, void **stream);
+/* Static facts of the loaded scene / selected kernel (for reports). */
+typedef struct mm_scene_info {
+    uint32_t n_planes, n_nodes, bvh_depth, max_leaf;
+    uint32_t nodes_in_shared;   /* 1 when the traversal reads child pairs from shared memory          */
+    uint32_t fast_slab_ok;      /* 1 when scene bounds allow the shared-reciprocal exact slab test    */
+    uint32_t smem_bytes, block_threads, blocks_per_sm, n_sms;
+} mm_scene_info;
+int mm_get_scene_info(mm_ctx *ctx, mm_scene_info *out);
+
+/* ---- Host surface kept from the reference (restated in C++; no device work) ------------------------- */
+
+/*
+ * Maze -> walls -> planes/materials/emissions -> BVH, as main() does once at start (main.rs:357-588),
+ * generalised from the hard-wired 10x10 to n x n.  Arrays are owned by the scene object.
+ */
+typedef struct mm_scene mm_scene;
+int mm_scene_build(uint32_t maze_n, uint64_t seed, int fast_bvh, mm_scene **out);
+int mm_scene_free(mm_scene *s);
+uint32_t mm_scene_n_planes(const mm_scene *s);
+uint32_t mm_scene_n_nodes(const mm_scene *s);
+const mm_plane    *mm_scene_planes(const mm_scene *s);
+const mm_bvh_node *mm_scene_nodes(const mm_scene *s);
+const uint32_t    *mm_scene_indices(const mm_scene *s);
+const uint8_t     *mm_scene_materials(const mm_scene *s);
+const mm_float4   *mm_scene_emissions(const mm_scene *s);
+const uint8_t     *mm_scene_grid(const mm_scene *s);       /* n*n passage bits, row-major [y][x] (main.rs:388-394) */
+uint32_t mm_scene_n_vert_walls(const mm_scene *s);
+uint32_t mm_scene_n_hori_walls(const mm_scene *s);
+const float *mm_scene_vert_walls(const mm_scene *s);       /* 3 floats each (x, start, len)   main.rs:409,416 */
+const float *mm_scene_hori_walls(const mm_scene *s);       /* 3 floats each (y, start, len)   main.rs:431,437 */
+
+/* build_bvh alone (main.rs:247-263) on caller planes; nodes must hold 2n-1 entries, indices n. */
+int mm_build_bvh(const mm_plane *planes, uint32_t n, int fast, mm_bvh_node *nodes, uint32_t *n_nodes_out,
+                 uint32_t *indices);
+
+/* rand 0.8.5 StdRng (ChaCha12) restatement used by the maze (main.rs:381-382,460,467,494,501). */
+typedef struct mm_stdrng mm_stdrng;
+int mm_stdrng_new(uint64_t seed, mm_stdrng **out);
+int mm_stdrng_free(mm_stdrng *r);
+uint32_t mm_stdrng_next_u32(mm_stdrng *r);
+float mm_stdrng_gen_f32(mm_stdrng *r);
+uint32_t mm_stdrng_gen_range_u32(mm_stdrng *r, uint32_t low, uint32_t high);
+/* Raw ChaCha block function with `rounds` rounds (8/12/20), 64-bit counter, 64-bit stream id. */
+int mm_chacha_block(const uint8_t key[32], uint64_t counter, uint64_t stream, int rounds, uint32_t out[16]);
+
+/* maths.rs:139-162, 175-178 */
+mm_float4 mm_calculate_quaternion(mm_float3 dir);
+mm_float4 mm_update_quat_angle(mm_float4 q, float theta);
+mm_float3 mm_quat_mult(mm_float3 v, mm_float4 q);
+
+/* gen_pixels without the shuffle (main.rs:293-302): x-major outer, y inner.  Returns the count written. */
+uint32_t mm_gen_chunks(float view_width, float view_height, uint32_t chunk_width, mm_chunk *out, uint32_t cap);
+/* Start-of-run camera and uniform as main.rs:732-755, generalised to an n x n maze. */
+int mm_default_uniform(uint32_t maze_n, float view_width, float view_height, uint32_t chunk_width,
+                       uint32_t time, mm_uniform *out);
+
+/* f-3 (SURVEY §8 f): player-box collision walk, main.rs:265-291. Returns node index or -1. */
+int mm_check_collision(const mm_bvh_node *nodes, uint32_t n_nodes, mm_float3 bmin, mm_float3 bmax);
+
+const char *mm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIRROR_MAZE_CUDA_H */

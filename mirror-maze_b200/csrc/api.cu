@@ -1,0 +1,408 @@
+// api.cu — implementation of the device half of include/mirror_maze_cuda.h: context, scene upload, dispatch.
+// Stands where the reference's Metal glue stood (reference src/utils.rs:14-102, src/main.rs:616-730, 861-894).
+// No CPU fallback exists: every entry point fails with MM_ERR_CUDA when no sm_100-class device is usable.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include "render_kernel.cuh"
+#include "scene_prep.h"
+
+using namespace mmk;
+
+struct mm_ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;       // stream in use
+    cudaStream_t own_stream = nullptr;   // created by mm_create
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    std::string err;
+    int n_sms = 0;
+    size_t smem_optin = 0;
+    // scene
+    bool have_scene = false;
+    Pair *d_pairs = nullptr;
+    RectI *d_rects = nullptr;
+    RectS *d_shade = nullptr;
+    uint8_t *d_noise = nullptr;
+    uint32_t n_pairs = 0, n_slots = 0, n_nodes = 0, root_link = 0, root_count = 0, depth = 0, max_leaf = 0, noise_w = 0, noise_h = 0;
+    bool fast_ok = false;
+    // per-frame
+    mm_chunk *d_chunks = nullptr;
+    uint32_t chunks_cap = 0, n_chunks = 0;
+    Counters *d_counters = nullptr;
+    Counters *h_counters = nullptr;   // pinned
+    float *d_screen = nullptr;        // persistent screen image (the reference's private screen texture, main.rs:702-709)
+    uint32_t screen_w = 0, screen_h = 0;
+    uint32_t *d_dbg_u32[3] = {nullptr, nullptr, nullptr};
+    float *d_dbg_rad = nullptr;
+    size_t dbg_cap = 0;
+    // last launch facts
+    uint32_t last_smem = 0, last_blocks_per_sm = 0;
+    bool last_smem_nodes = false;
+};
+
+static std::string g_create_err;
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                               \
+            return MM_ERR_CUDA;                                                                           \
+        }                                                                                                 \
+    } while (0)
+
+static int fail(mm_ctx *ctx, int code, const std::string &msg) {
+    ctx->err = msg;
+    return code;
+}
+
+static size_t smem_nodes_limit() {
+    // Child pairs are staged in shared memory when they fit beside the reduction scratch with at least two
+    // resident blocks per SM; larger trees are read through L1 (ld.global.nc).  MM_SMEM_NODE_LIMIT overrides (bytes).
+    const char *e = getenv("MM_SMEM_NODE_LIMIT");
+    if (e) return (size_t)strtoull(e, nullptr, 10);
+    return 100 * 1024;
+}
+
+extern "C" {
+
+int mm_create(int cuda_device, mm_ctx **out) {
+    if (!out) return MM_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return MM_ERR_CUDA;
+    }
+    if (cuda_device < 0 || cuda_device >= n) { g_create_err = "cuda_device out of range"; return MM_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cuda_device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return MM_ERR_CUDA; }
+    if (prop.major != 10) {
+        g_create_err = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "; this library is built for sm_100a only";
+        return MM_ERR_CUDA;
+    }
+    mm_ctx *ctx = new (std::nothrow) mm_ctx();
+    if (!ctx) return MM_ERR_NOMEM;
+    ctx->device = cuda_device;
+    ctx->n_sms = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    bool ok = cudaSetDevice(cuda_device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
+              cudaMalloc(&ctx->d_counters, sizeof(Counters)) == cudaSuccess &&
+              cudaMallocHost(&ctx->h_counters, sizeof(Counters)) == cudaSuccess;
+    if (!ok) {
+        g_create_err = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        mm_destroy(ctx);
+        return MM_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    memset(ctx->h_counters, 0, sizeof(Counters));
+    g_create_err.clear();
+    *out = ctx;
+    return MM_OK;
+}
+
+int mm_destroy(mm_ctx *ctx) {
+    if (!ctx) return MM_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_pairs); cudaFree(ctx->d_rects); cudaFree(ctx->d_shade); cudaFree(ctx->d_noise); cudaFree(ctx->d_chunks);
+    cudaFree(ctx->d_counters); cudaFree(ctx->d_screen); cudaFree(ctx->d_dbg_rad);
+    for (auto p : ctx->d_dbg_u32) cudaFree(p);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return MM_OK;
+}
+
+const char *mm_last_error(const mm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int mm_upload_scene(mm_ctx *ctx, const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *nodes, uint32_t n_nodes,
+                    const uint32_t *indices, const uint8_t *materials, const mm_float4 *emissions, const uint8_t *noise_rgba8,
+                    uint32_t noise_w, uint32_t noise_h) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!planes || !nodes || !indices || !materials || !emissions || !noise_rgba8 || n_planes == 0 || n_nodes == 0 || noise_w == 0 ||
+        noise_h == 0)
+        return fail(ctx, MM_ERR_INVALID, "mm_upload_scene: null pointer or zero size");
+    Prepared prep;
+    std::string perr;
+    int rc;
+    try {
+        rc = prepare_scene(planes, n_planes, nodes, n_nodes, indices, materials, emissions, prep, perr);
+    } catch (...) {
+        return fail(ctx, MM_ERR_NOMEM, "mm_upload_scene: out of host memory");
+    }
+    if (rc != MM_OK) return fail(ctx, rc, perr);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_scene = false;
+    cudaFree(ctx->d_pairs); cudaFree(ctx->d_rects); cudaFree(ctx->d_shade); cudaFree(ctx->d_noise);
+    ctx->d_pairs = nullptr; ctx->d_rects = nullptr; ctx->d_shade = nullptr; ctx->d_noise = nullptr;
+    const size_t noise_bytes = (size_t)noise_w * noise_h * 4;
+    CK(cudaMalloc(&ctx->d_pairs, prep.pairs.size() * sizeof(Pair)));
+    CK(cudaMalloc(&ctx->d_rects, prep.rects.size() * sizeof(RectI)));
+    CK(cudaMalloc(&ctx->d_shade, prep.shade.size() * sizeof(RectS)));
+    CK(cudaMalloc(&ctx->d_noise, noise_bytes));
+    CK(cudaMemcpyAsync(ctx->d_pairs, prep.pairs.data(), prep.pairs.size() * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_rects, prep.rects.data(), prep.rects.size() * sizeof(RectI), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_shade, prep.shade.data(), prep.shade.size() * sizeof(RectS), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_noise, noise_rgba8, noise_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_pairs = prep.n_pairs; ctx->n_slots = n_planes; ctx->n_nodes = n_nodes;
+    ctx->root_link = prep.root_link; ctx->root_count = prep.root_count;
+    ctx->depth = prep.depth; ctx->max_leaf = prep.max_leaf; ctx->fast_ok = prep.fast_ok;
+    ctx->noise_w = noise_w; ctx->noise_h = noise_h;
+    ctx->have_scene = true;
+    return MM_OK;
+}
+
+int mm_set_chunks(mm_ctx *ctx, const mm_chunk *chunks, uint32_t n_chunks) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!chunks || n_chunks == 0) return fail(ctx, MM_ERR_INVALID, "mm_set_chunks: null or empty chunk list");
+    CK(cudaSetDevice(ctx->device));
+    if (n_chunks > ctx->chunks_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_chunks);
+        ctx->d_chunks = nullptr; ctx->chunks_cap = 0;
+        CK(cudaMalloc(&ctx->d_chunks, (size_t)n_chunks * sizeof(mm_chunk)));
+        ctx->chunks_cap = n_chunks;
+    }
+    CK(cudaMemcpyAsync(ctx->d_chunks, chunks, (size_t)n_chunks * sizeof(mm_chunk), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_chunks = n_chunks;
+    return MM_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+struct Launch {
+    KParams p;
+    KernelChoice choice;
+    unsigned blocks;
+    size_t smem;
+};
+
+int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool debug, Launch &L) {
+    if (!uni || !par) return fail(ctx, MM_ERR_INVALID, "null uniform or params");
+    if (!ctx->have_scene) return fail(ctx, MM_ERR_NO_SCENE, "no scene uploaded");
+    const uint32_t spp = par->spp, chunk = uni->chunk_width;
+    if (spp == 0 || (spp & (spp - 1)) || spp > 256) return fail(ctx, MM_ERR_UNSUPPORTED, "spp must be a power of two in 1..256");
+    if (chunk == 0 || chunk > 64) return fail(ctx, MM_ERR_UNSUPPORTED, "chunk_width must be in 1..64");
+    const uint64_t T = (uint64_t)chunk * chunk * spp;
+    if (T > (1u << 20)) return fail(ctx, MM_ERR_UNSUPPORTED, "chunk_width^2 * spp too large");
+    if (par->grid_x == 0 || par->grid_y == 0) return fail(ctx, MM_ERR_INVALID, "empty grid");
+    const uint64_t n_groups = (uint64_t)par->grid_x * par->grid_y;
+    if (n_groups != ctx->n_chunks) return fail(ctx, MM_ERR_INVALID, "grid_x*grid_y must equal the chunk count");
+    if (par->bounce_limit > 4096 || par->mirror_limit > 4096) return fail(ctx, MM_ERR_INVALID, "bounce/mirror limit too large");
+    if (!(uni->view_width >= 1.0f) || !(uni->view_height >= 1.0f) || uni->view_width > 65536.0f || uni->view_height > 65536.0f)
+        return fail(ctx, MM_ERR_INVALID, "bad view size");
+    uint32_t first = par->group_first, step = par->group_step ? par->group_step : 1, count = par->group_count;
+    if (count == 0) { first = 0; step = 1; count = (uint32_t)n_groups; }
+    if ((uint64_t)first + (uint64_t)(count - 1) * step >= n_groups) return fail(ctx, MM_ERR_INVALID, "group range outside the grid");
+
+    KParams &p = L.p;
+    memset(&p, 0, sizeof(p));
+    p.uni = *uni;
+    p.spp = spp;
+    p.log2_spp = (uint32_t)__builtin_ctz(spp);
+    p.bounce_limit = (int32_t)par->bounce_limit;
+    p.mirror_limit = (int32_t)par->mirror_limit;
+    p.grid_x = par->grid_x; p.grid_y = par->grid_y;
+    p.group_first = first; p.group_step = step; p.group_count = count;
+    p.T = (uint32_t)T;
+    p.dim_x = p.T < 32 ? p.T : 32;
+    p.dim_y = p.T / p.dim_x;
+    p.ppc = chunk * chunk;
+    p.W = (uint32_t)uni->view_width; p.H = (uint32_t)uni->view_height;
+    p.n_pairs = ctx->n_pairs; p.n_slots = ctx->n_slots;
+    p.root_link = ctx->root_link; p.root_count = ctx->root_count;
+    p.noise_w = ctx->noise_w; p.noise_h = ctx->noise_h;
+    p.force_literal = (par->flags & MM_FLAG_FORCE_LITERAL) ? 1u : 0u;
+    p.scene_fast_ok = ctx->fast_ok ? 1u : 0u;
+    p.total_paths = (uint64_t)count * T;
+    p.pairs = ctx->d_pairs; p.rects = ctx->d_rects; p.shade = ctx->d_shade;
+    p.chunks = ctx->d_chunks; p.noise = ctx->d_noise;
+    p.counters = ctx->d_counters;
+
+    const size_t red_bytes = 3 * kBlockThreads * sizeof(float);
+    const size_t pair_bytes = (size_t)ctx->n_pairs * sizeof(Pair);
+    bool smem_nodes = ctx->n_pairs > 0 && !(par->flags & MM_FLAG_FORCE_GLOBAL) && pair_bytes <= smem_nodes_limit() &&
+                      red_bytes + pair_bytes <= ctx->smem_optin;
+    L.choice.smem_nodes = smem_nodes;
+    L.choice.debug = debug;
+    L.choice.counters = debug || (par->flags & MM_FLAG_COUNTERS);
+    L.smem = red_bytes + (smem_nodes ? pair_bytes : 0);
+    const uint64_t blocks = (p.total_paths + kBlockThreads - 1) / kBlockThreads;
+    if (blocks > 0x7FFFFFFFull) return fail(ctx, MM_ERR_UNSUPPORTED, "too many paths for one launch");
+    L.blocks = (unsigned)blocks;
+    return MM_OK;
+}
+
+int do_launch(mm_ctx *ctx, Launch &L) {
+    const void *fn = kernel_ptr(L.choice);
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlockThreads, L.smem));
+    ctx->last_blocks_per_sm = (uint32_t)per_sm;
+    ctx->last_smem = (uint32_t)L.smem;
+    ctx->last_smem_nodes = L.choice.smem_nodes;
+    CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->stream));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(launch_trace(L.p, L.choice, L.blocks, L.smem, ctx->stream));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->timed = true;
+    return MM_OK;
+}
+
+int ensure_screen(mm_ctx *ctx, uint32_t W, uint32_t H) {
+    if (ctx->d_screen && ctx->screen_w == W && ctx->screen_h == H) return MM_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_screen);
+    ctx->d_screen = nullptr;
+    CK(cudaMalloc(&ctx->d_screen, (size_t)W * H * 4 * sizeof(float)));
+    CK(cudaMemsetAsync(ctx->d_screen, 0, (size_t)W * H * 4 * sizeof(float), ctx->stream));
+    ctx->screen_w = W; ctx->screen_h = H;
+    return MM_OK;
+}
+
+void counters_out(const Counters *h, mm_counters *o) {
+    o->paths = h->paths; o->rays = h->rays; o->inner_visits = h->inner_visits; o->leaf_visits = h->leaf_visits;
+    o->rect_tests = h->rect_tests; o->hits = h->hits; o->literal_rays = h->literal_rays; o->max_stack = h->max_stack;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mm_render_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, float *d_image, float *d_tiles) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!d_image && !d_tiles) return fail(ctx, MM_ERR_INVALID, "mm_render_device: both outputs are null");
+    CK(cudaSetDevice(ctx->device));
+    Launch L;
+    int rc = build_launch(ctx, uni, params, false, L);
+    if (rc != MM_OK) return rc;
+    L.p.image = d_image;
+    L.p.tiles = d_tiles;
+    return do_launch(ctx, L);
+}
+
+int mm_render(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, const mm_chunk *chunks, uint32_t n_chunks,
+              float *out_rgba, mm_counters *counters, const mm_debug *debug) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!out_rgba) return fail(ctx, MM_ERR_INVALID, "mm_render: null output");
+    int rc = mm_set_chunks(ctx, chunks, n_chunks);
+    if (rc != MM_OK) return rc;
+    const bool dbg = debug && (debug->first_hit || debug->segments || debug->mirror_hits || debug->radiance);
+    Launch L;
+    rc = build_launch(ctx, uni, params, dbg, L);
+    if (rc != MM_OK) return rc;
+    rc = ensure_screen(ctx, L.p.W, L.p.H);
+    if (rc != MM_OK) return rc;
+    L.p.image = ctx->d_screen;
+    const size_t n_paths = (size_t)L.p.total_paths;
+    if (dbg) {
+        if (n_paths > ctx->dbg_cap) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (auto &p : ctx->d_dbg_u32) { cudaFree(p); p = nullptr; }
+            cudaFree(ctx->d_dbg_rad); ctx->d_dbg_rad = nullptr; ctx->dbg_cap = 0;
+            for (auto &p : ctx->d_dbg_u32) CK(cudaMalloc(&p, n_paths * sizeof(uint32_t)));
+            CK(cudaMalloc(&ctx->d_dbg_rad, n_paths * 3 * sizeof(float)));
+            ctx->dbg_cap = n_paths;
+        }
+        L.p.dbg_first_hit = debug->first_hit ? ctx->d_dbg_u32[0] : nullptr;
+        L.p.dbg_segments = debug->segments ? ctx->d_dbg_u32[1] : nullptr;
+        L.p.dbg_mirror_hits = debug->mirror_hits ? ctx->d_dbg_u32[2] : nullptr;
+        L.p.dbg_radiance = debug->radiance ? ctx->d_dbg_rad : nullptr;
+    }
+    rc = do_launch(ctx, L);
+    if (rc != MM_OK) return rc;
+    CK(cudaMemcpyAsync(out_rgba, ctx->d_screen, (size_t)L.p.W * L.p.H * 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dbg) {
+        if (debug->first_hit) CK(cudaMemcpyAsync(debug->first_hit, ctx->d_dbg_u32[0], n_paths * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (debug->segments) CK(cudaMemcpyAsync(debug->segments, ctx->d_dbg_u32[1], n_paths * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (debug->mirror_hits) CK(cudaMemcpyAsync(debug->mirror_hits, ctx->d_dbg_u32[2], n_paths * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (debug->radiance) CK(cudaMemcpyAsync(debug->radiance, ctx->d_dbg_rad, n_paths * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (counters) counters_out(ctx->h_counters, counters);
+    return MM_OK;
+}
+
+int mm_scatter_tiles_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, const float *d_tiles, float *d_image) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!uni || !params || !d_tiles || !d_image) return fail(ctx, MM_ERR_INVALID, "mm_scatter_tiles_device: null argument");
+    if (!ctx->d_chunks) return fail(ctx, MM_ERR_INVALID, "mm_scatter_tiles_device: no chunk list set");
+    const uint64_t n_groups = (uint64_t)params->grid_x * params->grid_y;
+    if (n_groups != ctx->n_chunks) return fail(ctx, MM_ERR_INVALID, "grid_x*grid_y must equal the chunk count");
+    uint32_t first = params->group_first, step = params->group_step ? params->group_step : 1, count = params->group_count;
+    if (count == 0) { first = 0; step = 1; count = (uint32_t)n_groups; }
+    if ((uint64_t)first + (uint64_t)(count - 1) * step >= n_groups) return fail(ctx, MM_ERR_INVALID, "group range outside the grid");
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_scatter(d_tiles, d_image, ctx->d_chunks, (uint32_t)n_groups, first, step, count, uni->chunk_width, (uint32_t)uni->view_width,
+                      (uint32_t)uni->view_height, ctx->stream));
+    return MM_OK;
+}
+
+int mm_sync(mm_ctx *ctx) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MM_OK;
+}
+
+int mm_set_stream(mm_ctx *ctx, void *stream) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    return MM_OK;
+}
+
+int mm_last_counters(mm_ctx *ctx, mm_counters *out) {
+    if (!ctx || !out) return MM_ERR_INVALID;
+    counters_out(ctx->h_counters, out);
+    return MM_OK;
+}
+
+int mm_last_ms(mm_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!ctx->timed) return fail(ctx, MM_ERR_INVALID, "mm_last_ms: nothing rendered yet");
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return MM_OK;
+}
+
+int mm_stream(mm_ctx *ctx, void **stream) {
+    if (!ctx || !stream) return MM_ERR_INVALID;
+    *stream = (void *)ctx->stream;
+    return MM_OK;
+}
+
+int mm_get_scene_info(mm_ctx *ctx, mm_scene_info *out) {
+    if (!ctx || !out) return MM_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, MM_ERR_NO_SCENE, "no scene uploaded");
+    out->n_planes = ctx->n_slots; out->n_nodes = ctx->n_nodes; out->bvh_depth = ctx->depth; out->max_leaf = ctx->max_leaf;
+    out->nodes_in_shared = ctx->last_smem_nodes ? 1u : 0u;
+    out->fast_slab_ok = ctx->fast_ok ? 1u : 0u;
+    out->smem_bytes = ctx->last_smem; out->block_threads = kBlockThreads; out->blocks_per_sm = ctx->last_blocks_per_sm;
+    out->n_sms = (uint32_t)ctx->n_sms;
+    return MM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,416 @@
+// render_kernel.cu — the hot path: mirror-maze's per-pixel path-tracing kernel, hand-written for sm_100a.
+//
+// One CUDA thread = one Metal thread of the reference's `compute_shader` (reference src/shaders.metal:245-368):
+// one (pixel, sample) path through ray generation (:281-284), seed + jitter (:291,298,303), the bounce loop
+// (:306-340) around intersect_bvh_iterative (:115-156) with intersect_aabb (:87-95) and ray_rect_intersect
+// (:51-67), per-sample tone-map (:344) and the per-pixel reduction in the reference's summation order (:347-366).
+//
+// Arithmetic contract: every fp32 + - * / sqrt is one IEEE round-to-nearest operation, written
+// with explicit __f*_rn intrinsics so that no compiler flag can contract or approximate them.  Results are
+// bit-identical to oracle/mm_oracle.cpp.
+//
+// Slab test without twelve divides.  The literal test divides (bound - origin) by the ray direction twelve times
+// per interior node.  In the common case the same correctly rounded quotients are produced from one IEEE
+// reciprocal per axis per ray: with r = RN(1/d), rho = 1 - d*r (exact by FMA), rl = RN(rho*r),
+//     q1 = RN(x*r + RN(x*rl))      error < 1/2 ulp + 2^-23 ulp  (faithful)
+//     e  = x - d*q1                exact by FMA
+//     q  = RN(q1 + e*r)            == RN(x/d)   (Markstein's theorem: r = RN(1/d), q1 faithful, no over/underflow)
+// The no-over/underflow side conditions are guaranteed by range checks: the scene's box coordinates are 0 or in
+// [2^-10, 2^30] (checked at upload) and a ray uses this path only when every |d| is in [2^-60, 2^60] and every
+// |origin| is 0 or in [2^-40, 2^30]; any other ray (zero / denormal / huge / NaN components) takes the literal
+// __fdiv_rn traversal, so the union is exact for all inputs.  MM_FLAG_FORCE_LITERAL disables the fast path.
+#include "render_kernel.cuh"
+
+namespace mmk {
+namespace {
+
+struct V3 { float x, y, z; };
+
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 add3(V3 a, V3 b) { return mk(fadd(a.x, b.x), fadd(a.y, b.y), fadd(a.z, b.z)); }
+__device__ __forceinline__ V3 sub3(V3 a, V3 b) { return mk(fsub(a.x, b.x), fsub(a.y, b.y), fsub(a.z, b.z)); }
+__device__ __forceinline__ V3 mul3(V3 a, V3 b) { return mk(fmul(a.x, b.x), fmul(a.y, b.y), fmul(a.z, b.z)); }
+__device__ __forceinline__ V3 scale3(V3 a, float s) { return mk(fmul(a.x, s), fmul(a.y, s), fmul(a.z, s)); }
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return fadd(fadd(fmul(a.x, b.x), fmul(a.y, b.y)), fmul(a.z, b.z)); }
+__device__ __forceinline__ V3 cross3(V3 a, V3 b) {
+    return mk(fsub(fmul(a.y, b.z), fmul(a.z, b.y)), fsub(fmul(a.z, b.x), fmul(a.x, b.z)), fsub(fmul(a.x, b.y), fmul(a.y, b.x)));
+}
+__device__ __forceinline__ float length3(V3 a) { return fsqrt(dot3(a, a)); }
+__device__ __forceinline__ V3 normalize3(V3 a) { float l = length3(a); return mk(fdiv(a.x, l), fdiv(a.y, l), fdiv(a.z, l)); }
+__device__ __forceinline__ V3 reflect3(V3 i, V3 n) { return sub3(i, scale3(n, fmul(2.0f, dot3(n, i)))); }
+__device__ __forceinline__ float sign1(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+
+// shaders.metal:181-186
+__device__ __forceinline__ float random_f(uint32_t &state) {
+    state = state * 747796405u + 291336453u;
+    uint32_t result = ((state >> ((state >> 28) + 4u)) ^ state) * 277803737u;
+    result = (result >> 22) ^ result;
+    return fmul(__uint2float_rn(result), 2.3283064365386963e-10f);   // float(result) / 2^32, exact scaling
+}
+__device__ __forceinline__ float rnd_pm1(uint32_t &state) { return fmul(fsub(random_f(state), 0.5f), 2.0f); }
+
+// shaders.metal:163-172
+struct Q4 { float x, y, z, w; };
+__device__ __forceinline__ Q4 quat_dot(Q4 q1, Q4 q2) {
+    V3 a = mk(q1.x, q1.y, q1.z), b = mk(q2.x, q2.y, q2.z);
+    float s = fsub(fmul(q1.w, q2.w), dot3(a, b));
+    V3 v = add3(add3(cross3(a, b), scale3(b, q1.w)), scale3(a, q2.w));
+    Q4 r = {v.x, v.y, v.z, s};
+    return r;
+}
+__device__ __forceinline__ V3 quat_mult(V3 vec, Q4 q) {
+    Q4 inv = {-q.x, -q.y, -q.z, q.w};
+    Q4 v4 = {vec.x, vec.y, vec.z, 0.0f};
+    Q4 r = quat_dot(quat_dot(inv, v4), q);
+    return mk(r.x, r.y, r.z);
+}
+
+struct Axis { float o, d, r, rl; };
+
+template <bool FAST>
+__device__ __forceinline__ float quot(float b, const Axis &a) {
+    float x = fsub(b, a.o);
+    if (FAST) {
+        float p = fmul(x, a.rl);
+        float q1 = __fmaf_rn(x, a.r, p);
+        float e = __fmaf_rn(-a.d, q1, x);
+        return __fmaf_rn(e, a.r, q1);
+    } else {
+        return fdiv(x, a.d);
+    }
+}
+
+__device__ __forceinline__ bool axis_safe(float o, float d) {
+    float ad = fabsf(d), ao = fabsf(o);
+    bool dok = ad >= 8.673617379884035e-19f /*2^-60*/ && ad <= 1.152921504606847e18f /*2^60*/;
+    bool ook = ao == 0.0f || (ao >= 9.094947017729282e-13f /*2^-40*/ && ao <= 1073741824.0f /*2^30*/);
+    return dok && ook;
+}
+
+struct Tally { uint32_t inner, leaf, rect, max_stack; };
+
+// shaders.metal:115-156 with :87-95 and :51-67 inlined.  `cur` descriptors: bits 0..23 link, 24..31 leaf count.
+template <bool FAST, bool CNT>
+__device__ __forceinline__ void traverse(const Pair *__restrict__ pairs, const RectI *__restrict__ rects, uint32_t root,
+                                         V3 ori, V3 dir, float &beam_t, uint32_t &beam_slot, uint32_t *stack, Tally &tl) {
+    Axis ax, ay, az;
+    ax.o = ori.x; ax.d = dir.x; ay.o = ori.y; ay.d = dir.y; az.o = ori.z; az.d = dir.z;
+    if (FAST) {
+        ax.r = __frcp_rn(ax.d); ax.rl = fmul(__fmaf_rn(-ax.d, ax.r, 1.0f), ax.r);
+        ay.r = __frcp_rn(ay.d); ay.rl = fmul(__fmaf_rn(-ay.d, ay.r, 1.0f), ay.r);
+        az.r = __frcp_rn(az.d); az.rl = fmul(__fmaf_rn(-az.d, az.r, 1.0f), az.r);
+    } else {
+        ax.r = ax.rl = ay.r = ay.rl = az.r = az.rl = 0.0f;
+    }
+    uint32_t cur = root;
+    uint32_t head = 0;
+    float t = beam_t;
+    uint32_t slot = beam_slot;
+    while (true) {
+        bool done = false;
+        while ((cur >> 24) == 0u) {
+            // interior: slab-test both children (shaders.metal:134-138)
+            const float4 *pp = reinterpret_cast<const float4 *>(pairs + cur);
+            float4 bx = pp[0], by = pp[1], bz = pp[2];
+            uint2 lk = *reinterpret_cast<const uint2 *>(pp + 3);
+            if (CNT) tl.inner++;
+            float dist1, dist2;
+            {
+                float t1 = quot<FAST>(bx.x, ax), t2 = quot<FAST>(bx.y, ax);
+                float tmin = fminf(t1, t2), tmax = fmaxf(t1, t2);
+                t1 = quot<FAST>(by.x, ay); t2 = quot<FAST>(by.y, ay);
+                tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
+                t1 = quot<FAST>(bz.x, az); t2 = quot<FAST>(bz.y, az);
+                tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
+                dist1 = (tmax >= tmin && tmin < t && tmax > 0.0f) ? tmin : 1e30f;
+            }
+            {
+                float t1 = quot<FAST>(bx.z, ax), t2 = quot<FAST>(bx.w, ax);
+                float tmin = fminf(t1, t2), tmax = fmaxf(t1, t2);
+                t1 = quot<FAST>(by.z, ay); t2 = quot<FAST>(by.w, ay);
+                tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
+                t1 = quot<FAST>(bz.z, az); t2 = quot<FAST>(bz.w, az);
+                tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
+                dist2 = (tmax >= tmin && tmin < t && tmax > 0.0f) ? tmin : 1e30f;
+            }
+            uint32_t near_d = lk.x, far_d = lk.y;
+            if (dist1 > dist2) {                                   // :140-148, ties keep the left child first
+                float tmp = dist1; dist1 = dist2; dist2 = tmp;
+                near_d = lk.y; far_d = lk.x;
+            }
+            if (dist1 == 1e30f) {                                  // :149-150
+                if (head == 0) { done = true; break; }
+                cur = stack[--head];
+            } else {                                               // :151-154
+                cur = near_d;
+                if (dist2 != 1e30f) {
+                    stack[head++] = far_d;
+                    if (CNT) tl.max_stack = max(tl.max_stack, head);
+                }
+            }
+        }
+        if (done) break;
+        // leaf: test every rect (shaders.metal:127-129)
+        uint32_t first = cur & 0xFFFFFFu, count = cur >> 24;
+        if (CNT) tl.leaf++;
+        for (uint32_t i = 0; i < count; i++) {
+            const float4 *rp = reinterpret_cast<const float4 *>(rects + first + i);
+            float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3];
+            if (CNT) tl.rect++;
+            V3 ro = mk(r0.x, r0.y, r0.z), n = mk(r1.x, r1.y, r1.z), v = mk(r2.x, r2.y, r2.z), u = mk(r3.x, r3.y, r3.z);
+            float len_v = r0.w, len_u = r1.w;
+            float norm_check = dot3(dir, n);                                   // :53
+            float a = fdiv(dot3(sub3(ro, ori), n), norm_check);                // :55
+            V3 isect = add3(ori, scale3(dir, a));                              // :56
+            V3 rv = sub3(isect, ro);                                           // :58
+            float d1 = fdiv(dot3(rv, v), len_v);                               // :60
+            float d2 = fdiv(dot3(rv, u), len_u);                               // :61
+            if ((0.0f <= d1 && d1 <= len_v) && (0.0f <= d2 && d2 <= len_u) && norm_check != 0.0f && a > 0.1f && a < t) {   // :63
+                t = a;
+                slot = first + i;
+            }
+        }
+        if (head == 0) break;
+        cur = stack[--head];
+    }
+    beam_t = t;
+    beam_slot = slot;
+}
+
+// noise.sample(s, float2(gid)): normalised coordinates, address::repeat, filter::nearest (shaders.metal:288,291).
+__device__ __forceinline__ void sample_noise_xy(const uint8_t *noise, uint32_t nw, uint32_t nh, float u, float v, float &nx, float &ny) {
+    float fu = fsub(u, floorf(u)), fv = fsub(v, floorf(v));
+    int ix = (int)floorf(fmul(fu, (float)nw)), iy = (int)floorf(fmul(fv, (float)nh));
+    ix = min(max(ix, 0), (int)nw - 1);
+    iy = min(max(iy, 0), (int)nh - 1);
+    const uint8_t *tx = noise + 4 * ((size_t)iy * nw + (size_t)ix);
+    uchar4 c = *reinterpret_cast<const uchar4 *>(tx);
+    nx = fdiv((float)c.x, 255.0f);
+    ny = fdiv((float)c.y, 255.0f);
+}
+
+template <bool SMEM_NODES, bool CNT, bool DBG>
+__global__ void __launch_bounds__(kBlockThreads)
+trace_kernel(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *red = reinterpret_cast<float *>(smem_raw);                      // 3 * kBlockThreads floats
+    const Pair *pairs = P.pairs;
+    if (SMEM_NODES) {
+        Pair *sp = reinterpret_cast<Pair *>(smem_raw + 3 * kBlockThreads * sizeof(float));
+        const float4 *src = reinterpret_cast<const float4 *>(P.pairs);
+        float4 *dst = reinterpret_cast<float4 *>(sp);
+        for (uint32_t i = threadIdx.x; i < P.n_pairs * 4u; i += kBlockThreads) dst[i] = src[i];
+        pairs = sp;
+        __syncthreads();
+    }
+
+    const uint64_t path = (uint64_t)blockIdx.x * kBlockThreads + threadIdx.x;
+    const bool active = path < P.total_paths;
+    uint32_t stack[MM_MAX_STACK];
+    Tally tl = {0u, 0u, 0u, 0u};
+    uint32_t seg = 0, nhits = 0, nliteral = 0;
+    V3 sample = mk(0.0f, 0.0f, 0.0f);
+    uint32_t pxx = 0, pxy = 0, k = 0, flat = 0;
+
+    if (active) {
+        k = (uint32_t)(path / P.T);
+        flat = (uint32_t)(path - (uint64_t)k * P.T);
+        const uint32_t g = P.group_first + k * P.group_step;
+        const uint32_t tgx = g % P.grid_x, tgy = g / P.grid_x;
+        const mm_chunk ch = P.chunks[g];                                   // :266-267
+        const uint32_t gx = flat % P.dim_x, gy = flat / P.dim_x;           // inverse of :271
+        const uint32_t chunk = P.uni.chunk_width;
+        const uint32_t pixel_number = flat >> P.log2_spp;                  // :272
+        pxx = ch.x + pixel_number / chunk;                                 // :274-275
+        pxy = ch.y + pixel_number % chunk;                                 // :273,275
+        const uint32_t texid_x = tgx * P.dim_x + gx, texid_y = tgy * P.dim_y + gy;
+
+        const mm_camera &cam = P.uni.cam;
+        const V3 center = mk(cam.camera_center.x, cam.camera_center.y, cam.camera_center.z);
+        const float pnx = fdiv(__uint2float_rn(pxx), P.uni.view_width), pny = fdiv(__uint2float_rn(pxy), P.uni.view_height);   // :281
+        const V3 corner = sub3(center, mk(fdiv(cam.viewport.x, 2.0f), fdiv(cam.viewport.y, 2.0f), -cam.focal_length));        // :282
+        V3 ray_dir = normalize3(sub3(add3(corner, mk(fmul(pnx, cam.viewport.x), fmul(pny, cam.viewport.y), 0.0f)), center));  // :283
+        const Q4 rot = {cam.rotation.x, cam.rotation.y, cam.rotation.z, cam.rotation.w};
+        ray_dir = quat_mult(ray_dir, rot);                                 // :284
+
+        float nx, ny;
+        sample_noise_xy(P.noise, P.noise_w, P.noise_h, __uint2float_rn(gx), __uint2float_rn(gy), nx, ny);   // :291
+        // :298 — float + uint promotes to float, products wrap in u32, left to right; float->uint saturates.
+        const float seed_f = fadd(fadd(fadd(fadd(nx, ny), __uint2float_rn(texid_x * 15823u)), __uint2float_rn(texid_y * 9737333u)),
+                                  __uint2float_rn(P.uni.time));
+        uint32_t state = __float2uint_rz(seed_f);
+
+        V3 ori = center;                                                   // :302
+        const float j1 = rnd_pm1(state), j2 = rnd_pm1(state);
+        V3 dir = add3(ray_dir, scale3(mk(j1, j2, 0.0f), 0.001f));          // :303
+        float t = 1e30f;
+        uint32_t slot = 0xFFFFFFFFu;
+        V3 color = mk(1.0f, 1.0f, 1.0f), light = mk(0.0f, 0.0f, 0.0f);
+        int mirror_hits = 0;
+        uint32_t first_hit = 0xFFFFFFFFu;
+
+        for (int n = 0; n < P.bounce_limit + mirror_hits; n++) {           // :306
+            const bool fast = !P.force_literal && P.scene_fast_ok && axis_safe(ori.x, dir.x) && axis_safe(ori.y, dir.y) &&
+                              axis_safe(ori.z, dir.z);
+            if (fast) {
+                traverse<true, CNT>(pairs, P.rects, P.root_link | (P.root_count << 24), ori, dir, t, slot, stack, tl);
+            } else {
+                traverse<false, CNT>(pairs, P.rects, P.root_link | (P.root_count << 24), ori, dir, t, slot, stack, tl);
+                nliteral++;
+            }
+            seg++;
+            if (!(t < 1e30f)) break;                                       // :308, :336-339 (sky term is * 0.0)
+            nhits++;
+            const float4 *rp = reinterpret_cast<const float4 *>(P.rects + slot);
+            const float4 r1 = rp[1], r2 = rp[2], r3 = rp[3];
+            if (DBG && n == 0) first_hit = __float_as_uint(r2.w);
+            const V3 nrm = mk(r1.x, r1.y, r1.z);                           // :309 (precomputed, same operations)
+            const float side = -sign1(dot3(dir, nrm));                     // :310
+            const float4 *sp4 = reinterpret_cast<const float4 *>(P.shade + slot);
+            if (__float_as_uint(r3.w) == 0u || side == -1.0f) {            // :311
+                const float4 col = sp4[0], emi = sp4[1];
+                light = add3(light, mul3(mk(emi.x, emi.y, emi.z), color)); // :312-313
+                color = mul3(color, mk(col.x, col.y, col.z));              // :314
+                V3 rd;
+                do {                                                       // :315-318
+                    float a = rnd_pm1(state), b = rnd_pm1(state), c = rnd_pm1(state);
+                    rd = mk(a, b, c);
+                } while (length3(rd) > 1.0f);
+                rd = normalize3(rd);                                       // :319
+                ori = add3(ori, scale3(dir, t));                           // :320
+                dir = normalize3(add3(rd, scale3(nrm, side)));             // :321
+                t = 1e30f;                                                 // :323
+            } else {
+                mirror_hits++;                                             // :325
+                if (mirror_hits < P.mirror_limit) {                        // :326
+                    const float4 col = sp4[0];
+                    light = add3(light, scale3(mk(col.x, col.y, col.z), 0.005f));   // :327
+                    ori = add3(ori, scale3(dir, t));                       // :328
+                    dir = normalize3(reflect3(dir, nrm));                  // :329
+                    t = 1e30f;                                             // :330
+                } else {
+                    break;                                                 // :333
+                }
+            }
+        }
+        sample = mk(fsqrt(fmaxf(light.x, 0.0f)), fsqrt(fmaxf(light.y, 0.0f)), fsqrt(fmaxf(light.z, 0.0f)));   // :344
+        if (DBG) {
+            if (P.dbg_first_hit) P.dbg_first_hit[path] = first_hit;
+            if (P.dbg_segments) P.dbg_segments[path] = seg;
+            if (P.dbg_mirror_hits) P.dbg_mirror_hits[path] = (uint32_t)mirror_hits;
+            if (P.dbg_radiance) { P.dbg_radiance[3 * path] = light.x; P.dbg_radiance[3 * path + 1] = light.y; P.dbg_radiance[3 * path + 2] = light.z; }
+        }
+    }
+
+    // Per-pixel reduction in the reference's order (shaders.metal:343-366): pairs, quads, octets (the phases whose
+    // stride is < spp), then the pixel's first thread adds the octets serially and divides by spp.
+    const uint32_t tid = threadIdx.x;
+    float *rx = red, *ry = red + kBlockThreads, *rz = red + 2 * kBlockThreads;
+    rx[tid] = sample.x; ry[tid] = sample.y; rz[tid] = sample.z;
+    __syncthreads();
+#pragma unroll
+    for (uint32_t stride = 1; stride <= 4; stride *= 2) {
+        if (stride < P.spp && (tid & (2 * stride - 1)) == 0) {
+            rx[tid] = fadd(rx[tid], rx[tid + stride]);
+            ry[tid] = fadd(ry[tid], ry[tid + stride]);
+            rz[tid] = fadd(rz[tid], rz[tid + stride]);
+        }
+        __syncthreads();
+    }
+    if (active && (flat & (P.spp - 1)) == 0) {
+        float sx = rx[tid], sy = ry[tid], sz = rz[tid];
+        for (uint32_t i = 1; i < P.spp / 8; i++) {
+            sx = fadd(sx, rx[tid + 8 * i]); sy = fadd(sy, ry[tid + 8 * i]); sz = fadd(sz, rz[tid + 8 * i]);
+        }
+        const float d = (float)(int)P.spp;
+        const float4 px = make_float4(fdiv(sx, d), fdiv(sy, d), fdiv(sz, d), 1.0f);
+        if (P.image && pxx < P.W && pxy < P.H) reinterpret_cast<float4 *>(P.image)[(size_t)pxy * P.W + pxx] = px;
+        if (P.tiles) reinterpret_cast<float4 *>(P.tiles)[(size_t)k * P.ppc + (flat >> P.log2_spp)] = px;
+    }
+
+    // Event counts: warp-reduce, one atomic per warp and counter.
+    {
+        unsigned long long v_rays = seg, v_hits = nhits, v_lit = nliteral, v_paths = active ? 1u : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v_rays += __shfl_xor_sync(0xFFFFFFFFu, v_rays, o);
+            v_hits += __shfl_xor_sync(0xFFFFFFFFu, v_hits, o);
+            v_lit += __shfl_xor_sync(0xFFFFFFFFu, v_lit, o);
+            v_paths += __shfl_xor_sync(0xFFFFFFFFu, v_paths, o);
+        }
+        unsigned long long v_inner = tl.inner, v_leaf = tl.leaf, v_rect = tl.rect;
+        uint32_t v_ms = tl.max_stack;
+        if (CNT) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                v_inner += __shfl_xor_sync(0xFFFFFFFFu, v_inner, o);
+                v_leaf += __shfl_xor_sync(0xFFFFFFFFu, v_leaf, o);
+                v_rect += __shfl_xor_sync(0xFFFFFFFFu, v_rect, o);
+                v_ms = max(v_ms, __shfl_xor_sync(0xFFFFFFFFu, v_ms, o));
+            }
+        }
+        if ((tid & 31u) == 0u) {
+            atomicAdd(&P.counters->rays, v_rays);
+            atomicAdd(&P.counters->hits, v_hits);
+            atomicAdd(&P.counters->paths, v_paths);
+            if (v_lit) atomicAdd(&P.counters->literal_rays, v_lit);
+            if (CNT) {
+                atomicAdd(&P.counters->inner_visits, v_inner);
+                atomicAdd(&P.counters->leaf_visits, v_leaf);
+                atomicAdd(&P.counters->rect_tests, v_rect);
+                atomicMax(&P.counters->max_stack, (unsigned long long)v_ms);
+            }
+        }
+    }
+}
+
+// De-interleave gathered tiles into the frame (consumer side of the multi-GPU tile gather).
+__global__ void scatter_kernel(const float4 *__restrict__ tiles, float4 *__restrict__ image, const mm_chunk *__restrict__ chunks,
+                               uint32_t group_first, uint32_t group_step, uint32_t group_count, uint32_t chunk, uint32_t ppc,
+                               uint32_t W, uint32_t H) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)group_count * ppc) return;
+    const uint32_t k = (uint32_t)(i / ppc), pn = (uint32_t)(i % ppc);
+    const mm_chunk ch = chunks[group_first + k * group_step];
+    const uint32_t x = ch.x + pn / chunk, y = ch.y + pn % chunk;
+    if (x < W && y < H) image[(size_t)y * W + x] = tiles[i];
+}
+
+template <bool S, bool C, bool D>
+const void *kptr() { return reinterpret_cast<const void *>(&trace_kernel<S, C, D>); }
+
+}  // namespace
+
+const void *kernel_ptr(KernelChoice c) {
+    if (c.smem_nodes) {
+        if (c.debug) return kptr<true, true, true>();
+        return c.counters ? kptr<true, true, false>() : kptr<true, false, false>();
+    }
+    if (c.debug) return kptr<false, true, true>();
+    return c.counters ? kptr<false, true, false>() : kptr<false, false, false>();
+}
+
+cudaError_t launch_trace(const KParams &p, KernelChoice c, unsigned blocks, size_t smem_bytes, cudaStream_t stream) {
+    const void *fn = kernel_ptr(c);
+    void *args[] = {const_cast<KParams *>(&p)};
+    return cudaLaunchKernel(fn, dim3(blocks), dim3(kBlockThreads), args, smem_bytes, stream);
+}
+
+cudaError_t launch_scatter(const float *tiles, float *image, const mm_chunk *chunks, uint32_t /*grid_groups*/, uint32_t group_first,
+                           uint32_t group_step, uint32_t group_count, uint32_t chunk, uint32_t W, uint32_t H, cudaStream_t stream) {
+    const uint32_t ppc = chunk * chunk;
+    const uint64_t n = (uint64_t)group_count * ppc;
+    if (n == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    scatter_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4 *>(tiles), reinterpret_cast<float4 *>(image), chunks,
+                                               group_first, group_step, group_count, chunk, ppc, W, H);
+    return cudaGetLastError();
+}
+
+}  // namespace mmk

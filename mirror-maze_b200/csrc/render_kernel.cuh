@@ -1,0 +1,79 @@
+// render_kernel.cuh — device data layout and kernel parameters shared by render_kernel.cu and api.cu.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/mirror_maze_cuda.h"
+
+namespace mmk {
+
+// One interior node's two children, 64 B, 64-B aligned (one 128-B line holds two pairs).
+// The reference node array (32 B each, children adjacent but only 32-B aligned; shaders.metal:30-35,134-135) is
+// re-laid per inner node so that one traversal step is four 16-B loads, one per slab axis plus the links:
+//   x = (c0.min.x, c0.max.x, c1.min.x, c1.max.x)   y, z likewise
+//   link = (c0.link, c0.count, c1.link, c1.count); count > 0: leaf, link = first slot in the leaf-ordered rect
+//   array; count == 0: interior, link = pair index of that child.
+struct __align__(16) Pair {
+    float4 x, y, z;
+    uint4 link;
+};
+static_assert(sizeof(Pair) == 64, "pair is 64 B");
+
+// One rectangle in leaf order (slot s = position in the reference `indices` array), 64 B.
+// The normal and the edge lengths are per-rect constants of ray_rect_intersect (shaders.metal:52,60-61); they are
+// evaluated once at upload with the same IEEE operations the literal code performs per call, hence bit-identical.
+struct __align__(16) RectI {
+    float4 o_lv;   // origin.xyz, length(v)
+    float4 n_lu;   // normalize(cross(v,u)).xyz, length(u)
+    float4 v_id;   // v.xyz, bits = original plane index
+    float4 u_mat;  // u.xyz, bits = material (0 matte, 1 mirror)
+};
+static_assert(sizeof(RectI) == 64, "rect is 64 B");
+
+// Shading constants per slot, 32 B: albedo and emissions.rgb * emissions.a (shaders.metal:312,314,327).
+struct __align__(16) RectS {
+    float4 color;    // rgb, unused
+    float4 emitted;  // rgb * a, unused
+};
+
+struct Counters {   // device-side mirror of mm_counters
+    unsigned long long paths, rays, inner_visits, leaf_visits, rect_tests, hits, literal_rays, max_stack;
+};
+
+struct KParams {
+    mm_uniform uni;            // the reference's 56-byte uniform, by value like set_bytes (main.rs:875-879)
+    uint32_t spp, log2_spp;
+    int32_t bounce_limit, mirror_limit;
+    uint32_t grid_x, grid_y;
+    uint32_t group_first, group_step, group_count;
+    uint32_t T;                // threads per virtual group = chunk^2 * spp
+    uint32_t dim_x, dim_y;     // virtual threads_per_threadgroup
+    uint32_t ppc;
+    uint32_t W, H;
+    uint32_t n_pairs, n_slots;
+    uint32_t root_link, root_count;   // descriptor of node 0 (pair 0 unless the root is a leaf)
+    uint32_t noise_w, noise_h;
+    uint32_t force_literal;
+    uint32_t scene_fast_ok;
+    uint64_t total_paths;
+    const Pair *pairs;
+    const RectI *rects;
+    const RectS *shade;
+    const mm_chunk *chunks;
+    const uint8_t *noise;
+    float *image;              // may be null
+    float *tiles;              // may be null
+    Counters *counters;
+    uint32_t *dbg_first_hit, *dbg_segments, *dbg_mirror_hits;
+    float *dbg_radiance;
+};
+
+constexpr int kBlockThreads = 256;
+
+// Returns the kernel's static properties for the occupancy query and launch.
+struct KernelChoice { bool smem_nodes, counters, debug; };
+const void *kernel_ptr(KernelChoice c);
+cudaError_t launch_trace(const KParams &p, KernelChoice c, unsigned blocks, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_scatter(const float *tiles, float *image, const mm_chunk *chunks, uint32_t grid_groups, uint32_t group_first,
+                           uint32_t group_step, uint32_t group_count, uint32_t chunk, uint32_t W, uint32_t H, cudaStream_t stream);
+
+}  // namespace mmk

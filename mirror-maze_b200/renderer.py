@@ -1,0 +1,189 @@
+"""Dispatch side of the drop-in: what the reference's frame loop does at src/main.rs:778-784 and 867-894
+(rewrite the chunk list, set the uniform, dispatch compute_shader, read the screen), through the C-ABI.
+
+Renderer          one context = one GPU = one stream (the reference has one device and one queue, main.rs:616-623).
+tile_partition    the multi-GPU split: interleaved groups of the virtual grid; seeds depend on the group index,
+                  not on the rank, so the union of all ranks' tiles is bit-identical to a one-GPU frame.
+TiledFrameRenderer  one process per GPU: render own tiles -> all-gather over NCCL (NVLink) -> scatter into the frame.
+
+No CPU fallback: constructing a Renderer without the built library or without a B200 raises MMError.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .abi import Counters, Debug, MMError, Params, SceneInfo, Uniform
+from .host import CHUNK_DTYPE, NODE_DTYPE, PLANE_DTYPE
+
+
+def tile_partition(n_groups, rank, world):
+    """(group_first, group_step, group_count) of `rank`: groups rank, rank+world, ... (load-balanced stripes)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank outside world")
+    count = (n_groups - rank + world - 1) // world if n_groups > rank else 0
+    return rank, world, count
+
+
+def scatter_tiles_host(tiles, chunks, first, step, count, chunk_width, image):
+    """Host twin of mm_scatter_tiles_device for callers that keep gathered tiles on the host:
+    tile k -> chunk of group first + k*step; pixel pn of a tile sits at (x + pn // chunk, y + pn % chunk)
+    (reference src/shaders.metal:272-275)."""
+    ppc = chunk_width * chunk_width
+    t = np.asarray(tiles, dtype=np.float32).reshape(-1, ppc, 4)
+    H, W = image.shape[:2]
+    pn = np.arange(ppc)
+    dx, dy = pn // chunk_width, pn % chunk_width
+    for k in range(count):
+        ch = chunks[first + k * step]
+        x, y = int(ch["x"]) + dx, int(ch["y"]) + dy
+        ok = (x < W) & (y < H)
+        image[y[ok], x[ok]] = t[k][ok]
+    return image
+
+
+class Renderer:
+    def __init__(self, device=0):
+        self._lib = abi.load_library()
+        self._ctx = C.c_void_p()
+        rc = self._lib.mm_create(device, C.byref(self._ctx))
+        if rc != 0:
+            raise MMError(rc, (self._lib.mm_last_error(None) or b"").decode())
+        self.device = device
+        self._chunks = None
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.mm_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MMError(rc, (self._lib.mm_last_error(self._ctx) or b"").decode())
+
+    # -- scene -------------------------------------------------------------------------------------------------
+    def upload_scene(self, scene, noise):
+        """make_buf x6 + noise texture (src/main.rs:667-695, 723-730)."""
+        planes = np.ascontiguousarray(scene.planes, dtype=PLANE_DTYPE)
+        nodes = np.ascontiguousarray(scene.nodes, dtype=NODE_DTYPE)
+        indices = np.ascontiguousarray(scene.indices, dtype=np.uint32)
+        materials = np.ascontiguousarray(scene.materials, dtype=np.uint8)
+        emissions = np.ascontiguousarray(scene.emissions, dtype=np.float32)
+        noise = np.ascontiguousarray(noise, dtype=np.uint8)
+        nh, nw = noise.shape[:2]
+        self._ck(self._lib.mm_upload_scene(self._ctx, planes.ctypes.data, len(planes), nodes.ctypes.data, len(nodes),
+                                           indices.ctypes.data, materials.ctypes.data, emissions.ctypes.data,
+                                           noise.ctypes.data, nw, nh))
+
+    def scene_info(self):
+        info = SceneInfo()
+        self._ck(self._lib.mm_get_scene_info(self._ctx, C.byref(info)))
+        return info.as_dict()
+
+    # -- host-buffer render (the reference-facing call) -------------------------------------------------------------
+    def render(self, uniform, params, chunks, out=None, debug=False):
+        """One dispatch with HOST buffers in and out.  Returns (image[H,W,4] float32, counters dict, debug dict|None)."""
+        chunks = np.ascontiguousarray(chunks, dtype=CHUNK_DTYPE)
+        H, W = int(uniform.view_height), int(uniform.view_width)
+        if out is None:
+            out = np.empty((H, W, 4), dtype=np.float32)
+        assert out.dtype == np.float32 and out.size == H * W * 4 and out.flags["C_CONTIGUOUS"]
+        cnt = Counters()
+        dbg_struct, dbg = None, None
+        if debug:
+            n_groups = params.group_count or params.grid_x * params.grid_y
+            n_paths = n_groups * uniform.chunk_width ** 2 * params.spp
+            dbg = {"first_hit": np.empty(n_paths, np.uint32), "segments": np.empty(n_paths, np.uint32),
+                   "mirror_hits": np.empty(n_paths, np.uint32), "radiance": np.empty((n_paths, 3), np.float32)}
+            dbg_struct = Debug(dbg["first_hit"].ctypes.data_as(C.POINTER(C.c_uint32)),
+                               dbg["segments"].ctypes.data_as(C.POINTER(C.c_uint32)),
+                               dbg["mirror_hits"].ctypes.data_as(C.POINTER(C.c_uint32)),
+                               dbg["radiance"].ctypes.data_as(C.POINTER(C.c_float)))
+        self._ck(self._lib.mm_render(self._ctx, C.byref(uniform), C.byref(params), chunks.ctypes.data, len(chunks),
+                                     out.ctypes.data, C.byref(cnt), C.byref(dbg_struct) if dbg_struct else None))
+        return out, cnt.as_dict(), dbg
+
+    def render_into(self, uniform, params, chunks_ptr, n_chunks, out_ptr):
+        """mm_render on raw host pointers (pinned buffers of the caller); returns counters dict."""
+        cnt = Counters()
+        self._ck(self._lib.mm_render(self._ctx, C.byref(uniform), C.byref(params), chunks_ptr, n_chunks, out_ptr,
+                                     C.byref(cnt), None))
+        return cnt.as_dict()
+
+    # -- device-resident path ------------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self._lib.mm_set_stream(self._ctx, cuda_stream_ptr))
+
+    def set_chunks(self, chunks):
+        chunks = np.ascontiguousarray(chunks, dtype=CHUNK_DTYPE)
+        self._chunks = chunks          # keep alive until the async copy has run
+        self._ck(self._lib.mm_set_chunks(self._ctx, chunks.ctypes.data, len(chunks)))
+
+    def render_device(self, uniform, params, image_ptr=None, tiles_ptr=None):
+        self._ck(self._lib.mm_render_device(self._ctx, C.byref(uniform), C.byref(params), image_ptr, tiles_ptr))
+
+    def scatter_tiles_device(self, uniform, params, tiles_ptr, image_ptr):
+        self._ck(self._lib.mm_scatter_tiles_device(self._ctx, C.byref(uniform), C.byref(params), tiles_ptr, image_ptr))
+
+    def sync(self):
+        self._ck(self._lib.mm_sync(self._ctx))
+
+    def last_counters(self):
+        cnt = Counters()
+        self._ck(self._lib.mm_last_counters(self._ctx, C.byref(cnt)))
+        return cnt.as_dict()
+
+    def last_ms(self):
+        ms = C.c_float()
+        self._ck(self._lib.mm_last_ms(self._ctx, C.byref(ms)))
+        return float(ms.value)
+
+
+class TiledFrameRenderer:
+    """One rank of the multi-GPU frame: scene replicated, groups interleaved over ranks, tiles all-gathered.
+
+    `dist` is torch.distributed (already initialised, backend nccl) or None for a single GPU.  Tensors are torch
+    CUDA tensors used purely as device memory; the kernels are this library's.
+    """
+
+    def __init__(self, renderer, uniform, params, chunks, rank=0, world=1, dist=None):
+        import torch
+
+        self.torch = torch
+        self.r = renderer
+        self.uniform = uniform
+        self.rank, self.world, self.dist = rank, world, dist
+        self.n_groups = params.grid_x * params.grid_y
+        self.ppc = uniform.chunk_width ** 2
+        self.H, self.W = int(uniform.view_height), int(uniform.view_width)
+        dev = torch.device("cuda", renderer.device)
+        self.parts = [tile_partition(self.n_groups, r, world) for r in range(world)]
+        self.max_count = max(p[2] for p in self.parts)
+        first, step, count = self.parts[rank]
+        self.my = Params.from_buffer_copy(bytes(params))
+        self.my.group_first, self.my.group_step, self.my.group_count = first, step, count
+        self.image = torch.zeros((self.H, self.W, 4), dtype=torch.float32, device=dev)
+        self.tiles = torch.zeros((self.max_count, self.ppc, 4), dtype=torch.float32, device=dev)
+        self.gathered = torch.zeros((world, self.max_count, self.ppc, 4), dtype=torch.float32, device=dev) if world > 1 else None
+        renderer.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        renderer.set_chunks(chunks)
+
+    def render_frame(self, uniform=None):
+        """Renders this rank's tiles, gathers everyone's, assembles the full frame on every rank (async)."""
+        u = uniform if uniform is not None else self.uniform
+        if self.world == 1:
+            self.r.render_device(u, self.my, image_ptr=self.image.data_ptr())
+            return self.image
+        if self.my.group_count:
+            self.r.render_device(u, self.my, tiles_ptr=self.tiles.data_ptr())
+        self.dist.all_gather_into_tensor(self.gathered, self.tiles)
+        for rk, (first, step, count) in enumerate(self.parts):
+            if count == 0:
+                continue
+            p = Params.from_buffer_copy(bytes(self.my))
+            p.group_first, p.group_step, p.group_count = first, step, count
+            self.r.scatter_tiles_device(u, p, self.gathered[rk].data_ptr(), self.image.data_ptr())
+        return self.image
