@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — measures BASELINE.json's metric (Mrays/s and ms/frame at 1080p x 16 spp, 8 bounces) on N B200s.
+
+A step = one frame of the hot path: every rank renders its interleaved share of the frame's 4x4-pixel chunks with the
+CUDA kernel, tiles are all-gathered over NCCL and scattered into the full frame on every rank (N = 1: the kernel writes
+the frame directly).  Total work per step is fixed as N grows ("strong" scaling: one frame, more GPUs).
+  value / ms_per_step : device time (CUDA events on the launching stream, max over ranks), inputs resident in HBM.
+  e2e                 : the same frame through the reference-facing C-ABI call with HOST buffers (mm_render at N = 1:
+                        chunk list + uniform host->device, kernel, whole frame device->host), wall clock.
+  roofline            : dominant kernel (trace_kernel) — algorithmic node/primitive bytes per launch (SURVEY §8 d:
+                        64 B per inner visit, 52 B per rect test, 65 B per shaded hit, 68 B in + 16/spp B out per path)
+                        over the kernel's CUDA-event duration, against the measured HBM copy peak as the contract
+                        asks; the scene is on-chip (shared memory / L1 / L2), so the binding limits are reported beside
+                        it: fp32_issue (algorithmic FP32-pipe ops vs SMs x 128 lanes x clock) and the achieved rates.
+  cpu_baseline        : the CPU oracle (oracle/mm_oracle.cpp, a port of the reference's shader) on the host cores, on a
+                        bounded interleaved crop of the same frame.
+--impl reference      : the reference's own CPU implementation of the path = that oracle port (the reference is a
+                        Metal shader + Rust host and cannot be compiled here), all host threads, rank 0 only.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/s @1080p x16spp, 8 bounces"
+UNIT = "Mrays/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--maze", type=int, default=32, help="maze size n (BASELINE configs[1]: 32; north-star headline: 64)")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--spp", type=int, default=16)
+    ap.add_argument("--bounces", type=int, default=8)
+    ap.add_argument("--mirror-limit", type=int, default=15)
+    ap.add_argument("--cpu-crop", type=int, default=4, help="cpu baseline renders every k-th chunk group")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="MM_FLAG_* for experiments (2 = literal divides, 4 = nodes in global)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"{a.maze}x{a.maze} Kruskal maze (seed 0), {a.width}x{a.height}, {a.spp} spp, {a.bounces} bounces "
+            f"(mirror_limit {a.mirror_limit}), chunk 4, start camera")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_work(cnt, spp):
+    """SURVEY §8(d) per-unit figures x the exact counters of one frame."""
+    bytes_ = 64 * cnt["inner_visits"] + 52 * cnt["rect_tests"] + 65 * cnt["hits"] + cnt["paths"] * (68 + 16 / spp)
+    fp32_ops = 50 * cnt["inner_visits"] + 84 * cnt["rect_tests"]          # 2 slab tests x 25 ops; rect: 75 flops + 3 sqrt + 6 div
+    return bytes_, fp32_ops
+
+
+def cpu_reference_run(a, steps, warmup, threads=0):
+    """Times the oracle port on the host cores over a bounded interleaved crop of the frame.  Returns (Mrays/s, info)."""
+    import mirror_maze_b200 as mm
+    from oracle import oracle
+
+    noise = mm.load_noise()
+    scene = mm.MazeScene(a.maze, 0)
+    u = mm.default_uniform(a.maze, a.width, a.height, 4)
+    chunks = mm.gen_chunks(a.width, a.height, 4)
+    p = mm.full_frame_params(u, spp=a.spp, bounce_limit=a.bounces, mirror_limit=a.mirror_limit)
+    n_groups = p.grid_x * p.grid_y
+    p.group_first, p.group_step = 0, max(1, a.cpu_crop)
+    p.group_count = (n_groups + p.group_step - 1) // p.group_step
+    cores = threads or oracle.num_threads()
+    import numpy as np
+
+    out = np.zeros((a.height, a.width, 4), dtype=np.float32)
+    times, rays = [], 0
+    for i in range(warmup + steps):
+        u.time = i
+        t0 = time.perf_counter()
+        _, cnt, _ = oracle.render(scene, noise, u, p, chunks, threads=cores, out=out)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt); rays += cnt["rays"]
+    total = sum(times)
+    sample = (f"every {p.group_step}th 4x4-chunk group of the frame ({p.group_count} of {n_groups} groups, "
+              f"{rays // max(1, steps)} rays per step), {steps} steps")
+    return rays / total / 1e6, {"cores": cores, "sample": sample, "ms_per_step": 1e3 * total / max(1, steps), "rays_per_step": rays // max(1, steps)}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps, warmup = max(1, min(a.steps, 3)), min(a.warmup, 1)          # bounded: each step is ~5-10 s of CPU work
+    val, info = cpu_reference_run(a, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": round(info["ms_per_step"], 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload_name(a), "note": "ms_per_step is for the bounded sample, not the whole frame"},
+            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]},
+            "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+
+    import mirror_maze_b200 as mm
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch N > 1 with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the render path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    noise = mm.load_noise()
+    scene = mm.MazeScene(a.maze, 0)
+    u = mm.default_uniform(a.maze, a.width, a.height, 4)
+    chunks = mm.gen_chunks(a.width, a.height, 4)
+    p = mm.full_frame_params(u, spp=a.spp, bounce_limit=a.bounces, mirror_limit=a.mirror_limit, flags=a.flags)
+    r = mm.Renderer(local)
+    r.upload_scene(scene, noise)
+    frame = mm.TiledFrameRenderer(r, u, p, chunks, rank=rank, world=world, dist=dist)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)        # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # exact event counts of this rank's share (deterministic; counted once with the counting kernel variant, untimed)
+    pc = mm.Params.from_buffer_copy(bytes(frame.my)); pc.flags = a.flags | mm.FLAG_COUNTERS
+    if pc.group_count:
+        r.render_device(u, pc, tiles_ptr=frame.tiles.data_ptr())
+    r.sync()
+    my_cnt = r.last_counters() if pc.group_count else {k: 0 for k in ("paths", "rays", "inner_visits", "leaf_visits", "rect_tests", "hits", "literal_rays", "max_stack")}
+
+    for i in range(a.warmup):
+        u.time = i
+        flush.fill_(i & 255)
+        frame.render_frame(u)
+    barrier()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    kernel_ms, rays_timed = [], 0
+    barrier()
+    for i in range(a.steps):
+        u.time = a.warmup + i
+        flush.fill_(i & 255)                       # L2 flush between timed iterations (outside the event pair)
+        if dist is not None:
+            dist.barrier()
+        ev[i][0].record()
+        frame.render_frame(u)
+        ev[i][1].record()
+        ev[i][1].synchronize()
+        if frame.my.group_count:
+            kernel_ms.append(r.last_ms())
+            rays_timed += r.last_counters()["rays"]
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    step_ms = [s.elapsed_time(e) for s, e in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    rays_all = torch.tensor([float(rays_timed)], dtype=torch.float64, device=dev)
+    cnt_vec = torch.tensor([float(my_cnt[k]) for k in ("paths", "rays", "inner_visits", "leaf_visits", "rect_tests", "hits", "literal_rays")],
+                           dtype=torch.float64, device=dev)
+    kms = torch.tensor([statistics.mean(kernel_ms) if kernel_ms else 0.0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays_all, op=dist.ReduceOp.SUM)
+        dist.all_reduce(cnt_vec, op=dist.ReduceOp.SUM)
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    total_ms, rays_all, kernel_mean_ms = float(total_ms.item()), float(rays_all.item()), float(kms.item())
+    cnt_frame = dict(zip(("paths", "rays", "inner_visits", "leaf_visits", "rect_tests", "hits", "literal_rays"), [int(v) for v in cnt_vec.tolist()]))
+
+    # ---- e2e: host buffers in, host frame out, wall clock ---------------------------------------------------------
+    H, W = a.height, a.width
+    host_frame = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    host_chunks = torch.from_numpy(chunks.view(np.uint32).reshape(-1, 2).copy()).pin_memory()
+    e2e_steps = max(3, min(a.steps, 10))
+    e2e_rays = 0
+    if world == 1:
+        r.set_stream(None)
+        for i in range(2):
+            r.render_into(u, p, host_chunks.data_ptr(), len(chunks), host_frame.data_ptr())
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            u.time = 1000 + i
+            c = r.render_into(u, p, host_chunks.data_ptr(), len(chunks), host_frame.data_ptr())
+            e2e_rays += c["rays"]
+        e2e_s = time.perf_counter() - t0
+        h2d = len(chunks) * 8 + ctypes.sizeof(mm.Uniform) + ctypes.sizeof(mm.Params)
+        d2h = H * W * 16 + ctypes.sizeof(mm.Counters)
+        e2e_launches = 1
+    else:
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            u.time = 1000 + i
+            r.set_chunks(chunks)                                   # host -> device every step, as the reference's copy_to_buf
+            img = frame.render_frame(u)
+            if rank == 0:
+                host_frame.copy_(img, non_blocking=True)           # assembled frame -> pinned host
+            torch.cuda.synchronize()
+            e2e_rays += r.last_counters()["rays"] if frame.my.group_count else 0
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_rays = float(tmax[0].item()), int(t[1].item())
+        h2d = len(chunks) * 8 + ctypes.sizeof(mm.Uniform) + ctypes.sizeof(mm.Params)
+        d2h = H * W * 16
+        e2e_launches = 1 + world
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    value = rays_all / (total_ms * 1e-3) / 1e6
+    ms_per_step = total_ms / a.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    alg_bytes, alg_ops = algorithmic_work(cnt_frame, a.spp)
+    # per launch: one launch per rank renders 1/world of the frame; the slowest rank's kernel time bounds the step
+    bytes_per_launch, ops_per_launch = alg_bytes / world, alg_ops / world
+    achieved_gbs = bytes_per_launch / (kernel_mean_ms * 1e-3) / 1e9 if kernel_mean_ms else 0.0
+    info = r.scene_info()
+    sm_max = (clocks or {}).get("sm_max_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    sm_now = (clocks or {}).get("sm_mhz") or sm_max
+    issue_peak_max = info["n_sms"] * 128 * sm_max * 1e6 / 1e12            # T lane-ops/s at max clock
+    issue_peak_now = info["n_sms"] * 128 * sm_now * 1e6 / 1e12            # at the clock seen under load
+    achieved_tops = ops_per_launch / (kernel_mean_ms * 1e-3) / 1e12 if kernel_mean_ms else 0.0
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = prof.get(f"maze{a.maze}", {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": round(achieved_gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved_gbs / hbm_peak, 4),
+                "traffic": traffic, "peak_source": peak_src, "kernel": "trace_kernel", "kernel_ms": round(kernel_mean_ms, 4),
+                "algorithmic_bytes_per_launch": int(bytes_per_launch),
+                "note": "scene is on-chip (smem/L1/L2): algorithmic node+primitive bytes are served by shared memory, not HBM; "
+                        "the binding limit is FP32 issue, reported in fp32_issue",
+                "fp32_issue": {"achieved": round(achieved_tops, 3), "peak": round(issue_peak_max, 2), "peak_at_load_clock": round(issue_peak_now, 2),
+                               "unit": "T lane-op/s", "frac": round(achieved_tops / issue_peak_max, 4),
+                               "frac_at_load_clock": round(achieved_tops / issue_peak_now, 4),
+                               "algorithmic_ops_per_launch": int(ops_per_launch),
+                               "def": "50 ops per inner visit (2 slab tests x 25, a divide = 1 op) + 84 per rect test (SURVEY 8d)"}}
+    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "paths_per_frame": cnt_frame["paths"], "rays_per_frame": cnt_frame["rays"],
+                       "parallelism": f"image tiles x{world} (interleaved 4x4-chunk groups), scene replicated" + (", NCCL all-gather" if world > 1 else ""),
+                       "l2_flush": "256 MiB device fill between timed iterations", "nodes_in_shared": info["nodes_in_shared"],
+                       "blocks_per_sm": info["blocks_per_sm"], "bvh_nodes": info["n_nodes"], "planes": info["n_planes"],
+                       "literal_rays_per_frame": cnt_frame["literal_rays"]},
+            "clocks": clocks, "roofline": roofline,
+            "e2e": {"value": round(e2e_rays / e2e_s / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": round(1e3 * e2e_s / e2e_steps, 4), "steps": e2e_steps,
+                    "api": "mm_render (host chunk list + uniform in, host frame out)" if world == 1 else
+                           "mm_set_chunks + mm_render_device + NCCL all-gather + mm_scatter_tiles_device + frame to pinned host on rank 0"},
+            "gpu_launches": a.steps * (1 if world == 1 else 1 + world), "counters": cnt_frame}
+    if not a.no_cpu_baseline and world == 1:
+        val, cinfo = cpu_reference_run(a, 1, 0)
+        line["cpu_baseline"] = {"value": round(val, 3), "unit": UNIT, "cores": cinfo["cores"], "kind": "port", "sample": cinfo["sample"]}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))

@@ -187,6 +187,13 @@ typedef struct mm_scene_info {
 } mm_scene_info;
 int mm_get_scene_info(mm_ctx *ctx, mm_scene_info *out);
 
+/*
+ * Self-test of the kernel's shared-reciprocal slab quotient (see render_kernel.cu header): evaluates n_pairs
+ * pseudo-random (x, d) pairs inside the guarded ranges, half of them adjacent to rounding midpoints, with both
+ * the fast sequence and __fdiv_rn, and returns how many differ (must be 0).
+ */
+int mm_selftest_quotient(mm_ctx *ctx, uint64_t n_pairs, uint64_t seed, uint64_t *mismatches);
+
 /* ---- Host surface kept from the reference (restated in C++; no device work) ------------------------- */
 
 /*

@@ -109,6 +109,7 @@ PROTOTYPES = {
     "mm_last_ms": (C.c_int, [_vp, _P(C.c_float)]),
     "mm_stream": (C.c_int, [_vp, _P(_vp)]),
     "mm_get_scene_info": (C.c_int, [_vp, _P(SceneInfo)]),
+    "mm_selftest_quotient": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _P(C.c_uint64)]),
     "mm_scene_build": (C.c_int, [C.c_uint32, C.c_uint64, C.c_int, _P(_vp)]),
     "mm_scene_free": (C.c_int, [_vp]),
     "mm_scene_n_planes": (C.c_uint32, [_vp]),

@@ -382,6 +382,49 @@ __global__ void scatter_kernel(const float4 *__restrict__ tiles, float4 *__restr
     if (x < W && y < H) image[(size_t)y * W + x] = tiles[i];
 }
 
+// Self-test of the shared-reciprocal quotient against __fdiv_rn on pseudo-random operands inside the guarded ranges
+// (|d| in [2^-60, 2^60], x = 0 or |x| in [2^-40, 2^31]); half of the samples are built to land within a few
+// 2^-24 ulp of a rounding midpoint, the only place where a faithful-but-not-exact quotient could differ.
+__device__ __forceinline__ uint32_t mix32(uint64_t &s) {
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    uint32_t x = (uint32_t)(((s >> 18) ^ s) >> 27), r = (uint32_t)(s >> 59);
+    return (x >> r) | (x << ((32 - r) & 31));
+}
+__global__ void quot_selftest_kernel(uint64_t n, uint64_t seed, unsigned long long *mismatches) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t s = seed ^ (tid * 0x9E3779B97F4A7C15ull);
+    unsigned long long bad = 0;
+    for (uint64_t i = tid; i < n; i += stride) {
+        const uint32_t a = mix32(s), b = mix32(s), c = mix32(s);
+        // d: random sign/mantissa, exponent in [-60, 59]
+        const int ed = (int)(a % 120u) - 60;
+        float d = __uint_as_float((b & 0x807FFFFFu) | ((uint32_t)(ed + 127) << 23));
+        float x;
+        if (c & 1u) {
+            // adversarial: x ~ (q + half ulp(q)) * d for a random q, so x/d sits next to a rounding midpoint
+            const uint32_t qm = mix32(s);
+            const int eq = (int)(qm % 40u) - 20;
+            float q = __uint_as_float((mix32(s) & 0x807FFFFFu) | ((uint32_t)(eq + 127) << 23));
+            double mid = (double)q + 0.5 * (double)(__uint_as_float(__float_as_uint(fabsf(q)) + 1u) - fabsf(q)) * (q < 0 ? -1.0 : 1.0);
+            x = (float)(mid * (double)d);
+            if ((c >> 1) & 1u) x = __uint_as_float(__float_as_uint(x) + ((c >> 2) & 3u) - 1u);   // +-1 ulp neighbours
+        } else {
+            const int ex = (int)((c >> 1) % 71u) - 40;
+            x = __uint_as_float((mix32(s) & 0x807FFFFFu) | ((uint32_t)(ex + 127) << 23));
+            if (((c >> 8) & 63u) == 0u) x = 0.0f;
+        }
+        const float ax = fabsf(x);
+        if (!(ax == 0.0f || (ax >= 9.094947017729282e-13f && ax <= 2147483648.0f))) continue;
+        Axis ax_;
+        ax_.o = 0.0f; ax_.d = d;
+        ax_.r = __frcp_rn(d); ax_.rl = fmul(__fmaf_rn(-d, ax_.r, 1.0f), ax_.r);
+        const float qf = quot<true>(x, ax_), ql = quot<false>(x, ax_);
+        const bool same = (__float_as_uint(qf) == __float_as_uint(ql)) || (qf == 0.0f && ql == 0.0f);
+        if (!same) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 template <bool S, bool C, bool D>
 const void *kptr() { return reinterpret_cast<const void *>(&trace_kernel<S, C, D>); }
 
@@ -400,6 +443,11 @@ cudaError_t launch_trace(const KParams &p, KernelChoice c, unsigned blocks, size
     const void *fn = kernel_ptr(c);
     void *args[] = {const_cast<KParams *>(&p)};
     return cudaLaunchKernel(fn, dim3(blocks), dim3(kBlockThreads), args, smem_bytes, stream);
+}
+
+cudaError_t launch_quot_selftest(uint64_t n, uint64_t seed, unsigned long long *d_mismatches, cudaStream_t stream) {
+    quot_selftest_kernel<<<148 * 8, 256, 0, stream>>>(n, seed, d_mismatches);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_scatter(const float *tiles, float *image, const mm_chunk *chunks, uint32_t /*grid_groups*/, uint32_t group_first,

@@ -136,6 +136,12 @@ class Renderer:
         self._ck(self._lib.mm_last_counters(self._ctx, C.byref(cnt)))
         return cnt.as_dict()
 
+    def selftest_quotient(self, n_pairs, seed=1):
+        """Mismatches between the shared-reciprocal slab quotient and __fdiv_rn over n_pairs samples (must be 0)."""
+        bad = C.c_uint64()
+        self._ck(self._lib.mm_selftest_quotient(self._ctx, n_pairs, seed, C.byref(bad)))
+        return int(bad.value)
+
     def last_ms(self):
         ms = C.c_float()
         self._ck(self._lib.mm_last_ms(self._ctx, C.byref(ms)))
@@ -167,7 +173,8 @@ class TiledFrameRenderer:
         self.my.group_first, self.my.group_step, self.my.group_count = first, step, count
         self.image = torch.zeros((self.H, self.W, 4), dtype=torch.float32, device=dev)
         self.tiles = torch.zeros((self.max_count, self.ppc, 4), dtype=torch.float32, device=dev)
-        self.gathered = torch.zeros((world, self.max_count, self.ppc, 4), dtype=torch.float32, device=dev) if world > 1 else None
+        # concatenated all-gather layout [world * max_count, ppc, 4]; rank r's tiles are rows r*max_count ...
+        self.gathered = torch.zeros((world * self.max_count, self.ppc, 4), dtype=torch.float32, device=dev) if world > 1 else None
         renderer.set_stream(torch.cuda.current_stream(dev).cuda_stream)
         renderer.set_chunks(chunks)
 
@@ -185,5 +192,5 @@ class TiledFrameRenderer:
                 continue
             p = Params.from_buffer_copy(bytes(self.my))
             p.group_first, p.group_step, p.group_count = first, step, count
-            self.r.scatter_tiles_device(u, p, self.gathered[rk].data_ptr(), self.image.data_ptr())
+            self.r.scatter_tiles_device(u, p, self.gathered[rk * self.max_count].data_ptr(), self.image.data_ptr())
         return self.image

@@ -1,0 +1,90 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/mirror_maze_cuda.h declares, keeps the
+reference's byte layouts (reference src/main.rs:32-90) and fails loudly — no fallback — without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mirror_maze_cuda.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_surface():
+    names = declared_functions()
+    for must in ("mm_create", "mm_destroy", "mm_upload_scene", "mm_render", "mm_render_device", "mm_scatter_tiles_device",
+                 "mm_set_chunks", "mm_sync", "mm_last_ms", "mm_last_error", "mm_scene_build", "mm_build_bvh"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(mm):
+    lib = C.CDLL(mm.library_path())
+    missing = [n for n in declared_functions() if not hasattr(lib, n)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+
+
+def test_binding_covers_every_declared_symbol(mm):
+    from mirror_maze_b200 import abi
+
+    assert sorted(abi.PROTOTYPES) == declared_functions()
+
+
+def test_struct_layouts_match_reference(mm):
+    assert C.sizeof(mm.Float2) == 8 and C.sizeof(mm.Float3) == 12 and C.sizeof(mm.Float4) == 16   # maths.rs:3-16,50-52
+    assert C.sizeof(mm.Plane) == 48                                                              # main.rs:51-58
+    assert [mm.Plane.origin.offset, mm.Plane.v.offset, mm.Plane.u.offset, mm.Plane.color.offset] == [0, 12, 24, 36]
+    assert C.sizeof(mm.BVHNode) == 32                                                            # main.rs:74-81
+    assert [mm.BVHNode.aabb_min.offset, mm.BVHNode.aabb_max.offset, mm.BVHNode.left_first.offset,
+            mm.BVHNode.tri_count.offset] == [0, 12, 24, 28]
+    assert C.sizeof(mm.Camera) == 40                                                             # main.rs:32-39
+    assert [mm.Camera.camera_center.offset, mm.Camera.focal_length.offset, mm.Camera.rotation.offset,
+            mm.Camera.viewport.offset] == [0, 12, 16, 32]
+    assert C.sizeof(mm.Uniform) == 56                                                            # main.rs:41-49
+    assert [mm.Uniform.cam.offset, mm.Uniform.view_width.offset, mm.Uniform.view_height.offset,
+            mm.Uniform.chunk_width.offset, mm.Uniform.time.offset] == [0, 40, 44, 48, 52]
+    assert C.sizeof(mm.Chunk) == 8
+
+
+def test_version_string(mm):
+    assert b"sm_100a" in mm.load_library().mm_version()
+
+
+def test_no_cpu_fallback_without_gpu(mm):
+    """On a box without a GPU the render path must refuse to exist, not degrade."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mm.MMError) as e:
+        mm.Renderer(0)
+    assert e.value.code == -2          # MM_ERR_CUDA
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_null_arguments_are_errors_not_crashes(mm):
+    lib = mm.load_library()
+    assert lib.mm_create(0, None) == -1
+    assert lib.mm_scene_build(0, 0, 1, None) == -1
+    h = C.c_void_p()
+    assert lib.mm_scene_build(0, 0, 1, C.byref(h)) == -1      # empty maze
+    assert lib.mm_sync(None) == -1
+    assert lib.mm_destroy(None) == 0
+    assert lib.mm_last_error(None) is not None
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through oracle/ (parity claims would be void)."""
+    pkg = os.path.join(ROOT, "mirror-maze_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".h", ".cuh")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                for needle in ("libmm_oracle", "from oracle", "import oracle", "np_oracle", "mmo_render", "oracle/_ref", "dlopen"):
+                    assert needle not in text, f"{f} references the oracle ({needle})"
+                assert not re.search(r'#include\s*["<][^">]*oracle', text), f"{f} includes oracle code"

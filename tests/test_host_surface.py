@@ -1,0 +1,162 @@
+"""Kept host surface (maze -> walls -> scene -> BVH -> camera/uniform/chunks), C++ restatement of reference
+src/main.rs:91-263, 293-302, 328-352, 357-588, 732-755 and src/maths.rs:139-178.  The reference has no tests, so
+these are: an independent Python restatement (oracle/host_ref.py) compared array for array, structural invariants
+(SURVEY §4), the reference's literals at its own size n = 10, and literal-vs-fast BVH builder equality."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+F = np.float32
+
+
+def planes_as_array(sc):
+    return np.stack([sc.planes["origin"], sc.planes["v"], sc.planes["u"], sc.planes["color"]], axis=1)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 10, 16])
+def test_cpp_matches_python_restatement(mm, n):
+    from oracle import host_ref
+
+    ref = host_ref.build_scene(n, 0)
+    sc = mm.MazeScene(n, 0, fast_bvh=False)
+    assert np.array_equal(ref["grid"], sc.grid)
+    assert np.array_equal(ref["vert"], sc.vert_walls) and np.array_equal(ref["hori"], sc.hori_walls)
+    assert planes_as_array(sc).tobytes() == ref["planes"].tobytes()
+    assert np.array_equal(ref["materials"], sc.materials)
+    assert ref["emissions"].tobytes() == sc.emissions.tobytes()
+    assert ref["nodes"].tobytes() == sc.nodes.tobytes()
+    assert np.array_equal(ref["indices"], sc.indices)
+
+
+@pytest.mark.parametrize("n,seed", [(5, 0), (10, 0), (16, 3), (32, 0), (48, 9)])
+def test_fast_bvh_builder_emits_the_literal_arrays(mm, n, seed):
+    a = mm.MazeScene(n, seed, fast_bvh=False)
+    b = mm.MazeScene(n, seed, fast_bvh=True)
+    assert a.nodes.tobytes() == b.nodes.tobytes()
+    assert np.array_equal(a.indices, b.indices)
+
+
+def test_fast_bvh_on_adversarial_planes(mm):
+    """Coincident centres, zero-area planes and equal costs exercise the `<=` tie rule (main.rs:123)."""
+    from mirror_maze_b200.host import PLANE_DTYPE, build_bvh
+
+    rng = np.random.default_rng(5)
+    P = np.zeros(300, dtype=PLANE_DTYPE)
+    P["origin"] = rng.integers(-4, 5, size=(300, 3)).astype(F) * F(10)
+    P["v"] = rng.integers(0, 3, size=(300, 3)).astype(F) * F(10) * (rng.integers(0, 2, size=(300, 3)))
+    P["u"] = rng.integers(-2, 1, size=(300, 3)).astype(F) * F(10) * (rng.integers(0, 2, size=(300, 3)))
+    na, ia = build_bvh(P, fast=False)
+    nb, ib = build_bvh(P, fast=True)
+    assert na.tobytes() == nb.tobytes() and np.array_equal(ia, ib)
+
+
+@pytest.mark.parametrize("n", [10, 16, 32, 64])
+def test_bvh_structural_invariants(scenes, n):
+    sc = scenes(n)
+    nodes, idx = sc.nodes, sc.indices
+    assert sorted(idx.tolist()) == list(range(sc.n_planes))               # a permutation
+    seen_planes = []
+    origin, u, v = sc.planes["origin"], sc.planes["u"], sc.planes["v"]
+    corners = np.stack([origin, origin + u, origin + v], axis=1)
+
+    def walk(i, depth):
+        nd = nodes[i]
+        if nd["tri_count"] > 0:
+            ids = idx[nd["left_first"]: nd["left_first"] + nd["tri_count"]]
+            seen_planes.extend(ids.tolist())
+            c = corners[ids].reshape(-1, 3)
+            assert np.array_equal(c.min(axis=0), nd["aabb_min"]) and np.array_equal(c.max(axis=0), nd["aabb_max"])
+            return depth
+        l, r = int(nd["left_first"]), int(nd["left_first"]) + 1           # children adjacent (main.rs:162-168)
+        assert l % 2 == 1 and r < len(nodes)
+        for c in (l, r):
+            assert (nodes[c]["aabb_min"] >= nd["aabb_min"]).all() and (nodes[c]["aabb_max"] <= nd["aabb_max"]).all()
+        return max(walk(l, depth + 1), walk(r, depth + 1))
+
+    depth = walk(0, 1)
+    assert sorted(seen_planes) == list(range(sc.n_planes))                # every plane in exactly one leaf
+    assert depth <= 48
+    assert len(nodes) % 2 == 1 and len(nodes) <= 2 * sc.n_planes - 1
+
+
+def test_reference_size_scene_literals(mm):
+    """At n = 10 the generalised scene must reproduce the reference's hard-wired numbers (main.rs:517-586, 735)."""
+    sc = mm.MazeScene(10, 0)
+    P = sc.planes
+    tail = P[-7:]
+    assert tail[0]["origin"].tolist() == [-50.0, 2.0, -50.0] and tail[0]["v"].tolist() == [0.0, -20.0, 0.0] and tail[0]["u"].tolist() == [100.0, 0.0, 0.0]
+    assert tail[1]["origin"].tolist() == [-50.0, 2.0, 50.0] and tail[1]["v"].tolist() == [100.0, 0.0, 0.0]
+    assert tail[2]["v"].tolist() == [0.0, 0.0, 100.0] and tail[3]["origin"].tolist() == [50.0, 2.0, -50.0]
+    assert tail[4]["v"].tolist() == [0.0, 0.0, -100.0] and np.allclose(tail[4]["color"], [0.4, 0.45, 0.3])
+    assert tail[5]["origin"][2] == F(-49.9) and tail[5]["origin"][0] == F(-5.0)        # entry light
+    assert tail[6]["origin"].tolist() == [-50.0, -8.0, 50.0]                            # roof
+    assert sc.emissions[-1].tolist() == [1.0, F(0.8), F(0.3), F(0.02)]
+    assert sc.emissions[-2].tolist() == [1.0, F(0.8), F(0.3), 2.0]
+    u = mm.default_uniform(10, 1024, 768, 4)
+    assert [u.cam.camera_center.x, u.cam.camera_center.y, u.cam.camera_center.z] == [-5.0, 0.0, -45.0]
+    assert u.cam.focal_length == 1.0 and u.cam.viewport.y == 2.0 and u.cam.viewport.x == F(2.0) * (F(1024) / F(768))
+
+
+def test_maze_is_a_spanning_tree(scenes):
+    for n in (10, 32):
+        g = scenes(n).grid
+        opened = sum(bin(int(c)).count("1") for c in g.ravel()) // 2
+        assert opened == n * n - 1                                         # Kruskal: exactly n^2 - 1 passages
+        for y in range(n):
+            for x in range(n):
+                if g[y, x] & 1: assert y > 0 and g[y - 1, x] & 2
+                if g[y, x] & 4: assert x > 0 and g[y, x - 1] & 8
+        # connectivity
+        seen, todo = {(0, 0)}, [(0, 0)]
+        while todo:
+            x, y = todo.pop()
+            for bit, dx, dy in ((1, 0, -1), (2, 0, 1), (4, -1, 0), (8, 1, 0)):
+                if g[y, x] & bit and (x + dx, y + dy) not in seen:
+                    seen.add((x + dx, y + dy)); todo.append((x + dx, y + dy))
+        assert len(seen) == n * n
+
+
+def test_walls_cover_closed_edges_and_keep_degenerate_runs(scenes):
+    sc = scenes(16)
+    n, g = 16, sc.grid
+    closed_v = sum(1 for x in range(1, n) for y in range(n) if not (g[y, x] & 4))
+    assert int(sc.vert_walls[sc.vert_walls[:, 0] > 0][:, 2].sum()) == closed_v
+    assert sc.vert_walls[0].tolist() == [0.0, 0.0, float(n)]                # x == 0: one full-height wall
+    assert (sc.vert_walls[:, 2] == 0).any() or (sc.hori_walls[:, 2] == 0).any()   # trailing zero-length runs are kept (:416,437)
+
+
+def test_scene_statistics_are_plausible(scenes):
+    sc = scenes(64)
+    walls = sc.emissions[:, 3] == 0.0
+    frac_mirror = sc.materials[walls].mean()
+    assert 0.05 < frac_mirror < 0.2                                        # 15 % / 10 % mirror odds (main.rs:460,494)
+    assert (sc.emissions[:, 3] == 2.0).sum() > 100                         # light panels on short walls
+
+
+def test_quaternion_and_camera(mm):
+    q = mm.calculate_quaternion([0.1, 0.0, 1.0])                          # main.rs:740
+    assert abs(float(np.linalg.norm(q)) - 1.0) < 1e-6 and q[0] == 0.0 and q[2] == 0.0 and q[1] > 0
+    ht = math.acos(float(q[3]))
+    assert abs(2 * ht - math.atan2(0.1, 1.0)) < 1e-5        # acos of an f32 near 1 loses bits
+    fwd = mm.quat_mult([0.0, 0.0, 1.0], q)
+    assert abs(float(np.linalg.norm(fwd)) - 1.0) < 1e-6
+    q2 = mm.update_quat_angle(q, 0.7)
+    assert abs(float(q2[3]) - math.cos(0.7)) < 1e-6 and abs(float(q2[1]) - math.sin(0.7)) < 1e-5
+
+
+def test_chunk_order_is_gen_pixels_without_shuffle(mm):
+    ch = mm.gen_chunks(16, 12, 4)
+    assert [(int(c["x"]), int(c["y"])) for c in ch] == [(4 * i, 4 * j) for i in range(4) for j in range(3)]   # main.rs:298-302
+    assert len(mm.gen_chunks(1920, 1080, 4)) == 480 * 270
+
+
+def test_check_collision(mm, scenes):
+    sc = scenes(10)
+    u = mm.default_uniform(10, 64, 64)
+    c = np.array([u.cam.camera_center.x, u.cam.camera_center.y, u.cam.camera_center.z], dtype=F)
+    d = np.array([0.5, 0.2, 0.5], dtype=F)                                 # player_diag main.rs:738
+    assert mm.check_collision(sc.nodes, c - d, c + d) == -1                # the start cell is free
+    wall_x = np.array([-50.0, 0.0, -45.0], dtype=F)                        # on the outer x = -50 wall
+    assert mm.check_collision(sc.nodes, wall_x - d, wall_x + d) >= 0
