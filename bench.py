@@ -200,6 +200,7 @@ def run_ours(a):
     r.sync()
     my_cnt = r.last_counters() if pc.group_count else {k: 0 for k in ("paths", "rays", "inner_visits", "leaf_visits", "rect_tests", "hits", "literal_rays", "max_stack")}
 
+    torch.cuda.set_stream(frame.stream)            # every torch op below (flush, events, collectives) shares the kernel's stream
     for i in range(a.warmup):
         u.time = i
         flush.fill_(i & 255)
@@ -247,7 +248,6 @@ def run_ours(a):
     e2e_steps = max(3, min(a.steps, 10))
     e2e_rays = 0
     if world == 1:
-        r.set_stream(None)
         for i in range(2):
             r.render_into(u, p, host_chunks.data_ptr(), len(chunks), host_frame.data_ptr())
         t0 = time.perf_counter()

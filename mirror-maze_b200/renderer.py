@@ -175,7 +175,10 @@ class TiledFrameRenderer:
         self.tiles = torch.zeros((self.max_count, self.ppc, 4), dtype=torch.float32, device=dev)
         # concatenated all-gather layout [world * max_count, ppc, 4]; rank r's tiles are rows r*max_count ...
         self.gathered = torch.zeros((world * self.max_count, self.ppc, 4), dtype=torch.float32, device=dev) if world > 1 else None
-        renderer.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        # One stream for the kernel, the collective and the scatter: a dedicated torch stream (the legacy default
+        # stream's handle is 0, which mm_set_stream reads as "use the context's own stream").
+        self.stream = torch.cuda.Stream(dev)
+        renderer.set_stream(self.stream.cuda_stream)
         renderer.set_chunks(chunks)
 
     def render_frame(self, uniform=None):
@@ -186,7 +189,8 @@ class TiledFrameRenderer:
             return self.image
         if self.my.group_count:
             self.r.render_device(u, self.my, tiles_ptr=self.tiles.data_ptr())
-        self.dist.all_gather_into_tensor(self.gathered, self.tiles)
+        with self.torch.cuda.stream(self.stream):
+            self.dist.all_gather_into_tensor(self.gathered, self.tiles)
         for rk, (first, step, count) in enumerate(self.parts):
             if count == 0:
                 continue

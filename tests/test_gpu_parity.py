@@ -113,23 +113,20 @@ def test_device_tiles_gather_and_scatter(mm, noise, scenes, renderer):
     dev = torch.device("cuda", 0)
     r2 = mm.Renderer(0)
     r2.upload_scene(sc, noise)
+    r2.set_chunks(ch)
     world = 4
-    frames = []
-    for rank in range(world):
-        fr = mm.TiledFrameRenderer(r2, u, p, ch, rank=rank, world=1)
-        fr.world, fr.parts = world, [mm.tile_partition(p.grid_x * p.grid_y, r, world) for r in range(world)]
-        frames.append(fr)
+    parts = [mm.tile_partition(p.grid_x * p.grid_y, r, world) for r in range(world)]
     ppc = u.chunk_width ** 2
-    max_count = max(pt[2] for pt in frames[0].parts)
+    max_count = max(pt[2] for pt in parts)
     gathered = torch.zeros((world, max_count, ppc, 4), dtype=torch.float32, device=dev)
     for rank in range(world):
         q = mm.Params.from_buffer_copy(bytes(p))
-        q.group_first, q.group_step, q.group_count = frames[0].parts[rank]
+        q.group_first, q.group_step, q.group_count = parts[rank]
         r2.render_device(u, q, tiles_ptr=gathered[rank].data_ptr())
     image = torch.zeros((int(u.view_height), int(u.view_width), 4), dtype=torch.float32, device=dev)
     for rank in range(world):
         q = mm.Params.from_buffer_copy(bytes(p))
-        q.group_first, q.group_step, q.group_count = frames[0].parts[rank]
+        q.group_first, q.group_step, q.group_count = parts[rank]
         r2.scatter_tiles_device(u, q, gathered[rank].data_ptr(), image.data_ptr())
     r2.sync()
     torch.cuda.synchronize()
