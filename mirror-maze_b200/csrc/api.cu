@@ -22,7 +22,7 @@ struct mm_ctx {
     size_t smem_optin = 0;
     // scene
     bool have_scene = false;
-    Pair *d_pairs = nullptr;
+    PairRec *d_pairs = nullptr;
     RectI *d_rects = nullptr;
     RectS *d_shade = nullptr;
     uint8_t *d_noise = nullptr;
@@ -64,7 +64,7 @@ static size_t smem_nodes_limit() {
     // resident blocks per SM; larger trees are read through L1 (ld.global.nc).  MM_SMEM_NODE_LIMIT overrides (bytes).
     const char *e = getenv("MM_SMEM_NODE_LIMIT");
     if (e) return (size_t)strtoull(e, nullptr, 10);
-    return 100 * 1024;
+    return 105 * 1024;
 }
 
 extern "C" {
@@ -146,11 +146,11 @@ int mm_upload_scene(mm_ctx *ctx, const mm_plane *planes, uint32_t n_planes, cons
     cudaFree(ctx->d_pairs); cudaFree(ctx->d_rects); cudaFree(ctx->d_shade); cudaFree(ctx->d_noise);
     ctx->d_pairs = nullptr; ctx->d_rects = nullptr; ctx->d_shade = nullptr; ctx->d_noise = nullptr;
     const size_t noise_bytes = (size_t)noise_w * noise_h * 4;
-    CK(cudaMalloc(&ctx->d_pairs, prep.pairs.size() * sizeof(Pair)));
+    CK(cudaMalloc(&ctx->d_pairs, prep.pairs.size() * sizeof(PairRec)));
     CK(cudaMalloc(&ctx->d_rects, prep.rects.size() * sizeof(RectI)));
     CK(cudaMalloc(&ctx->d_shade, prep.shade.size() * sizeof(RectS)));
     CK(cudaMalloc(&ctx->d_noise, noise_bytes));
-    CK(cudaMemcpyAsync(ctx->d_pairs, prep.pairs.data(), prep.pairs.size() * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_pairs, prep.pairs.data(), prep.pairs.size() * sizeof(PairRec), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_rects, prep.rects.data(), prep.rects.size() * sizeof(RectI), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_shade, prep.shade.data(), prep.shade.size() * sizeof(RectS), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_noise, noise_rgba8, noise_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -228,13 +228,20 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
     p.noise_w = ctx->noise_w; p.noise_h = ctx->noise_h;
     p.force_literal = (par->flags & MM_FLAG_FORCE_LITERAL) ? 1u : 0u;
     p.scene_fast_ok = ctx->fast_ok ? 1u : 0u;
+    p.th_inner = 16; p.w_inner = 1; p.w_leaf = 1; p.w_shade = 1;
+    if (const char *e = getenv("MM_SCHED")) {   // tuning hook: "th,wI,wL,wS"
+        unsigned a, b, c, d;
+        if (sscanf(e, "%u,%u,%u,%u", &a, &b, &c, &d) == 4 && a >= 1 && b >= 1 && c >= 1 && d >= 1) {   // th = 0 would never leave the loop
+            p.th_inner = a; p.w_inner = b; p.w_leaf = c; p.w_shade = d;
+        }
+    }
     p.total_paths = (uint64_t)count * T;
     p.pairs = ctx->d_pairs; p.rects = ctx->d_rects; p.shade = ctx->d_shade;
     p.chunks = ctx->d_chunks; p.noise = ctx->d_noise;
     p.counters = ctx->d_counters;
 
     const size_t red_bytes = 3 * kBlockThreads * sizeof(float);
-    const size_t pair_bytes = (size_t)ctx->n_pairs * sizeof(Pair);
+    const size_t pair_bytes = (size_t)ctx->n_pairs * kPairSmemBytes;
     bool smem_nodes = ctx->n_pairs > 0 && !(par->flags & MM_FLAG_FORCE_GLOBAL) && pair_bytes <= smem_nodes_limit() &&
                       red_bytes + pair_bytes <= ctx->smem_optin;
     L.choice.smem_nodes = smem_nodes;

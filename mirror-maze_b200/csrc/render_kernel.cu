@@ -95,89 +95,136 @@ __device__ __forceinline__ bool axis_safe(float o, float d) {
 
 struct Tally { uint32_t inner, leaf, rect, max_stack; };
 
-// shaders.metal:115-156 with :87-95 and :51-67 inlined.  `cur` descriptors: bits 0..23 link, 24..31 leaf count.
+// Where a lane's child pairs come from.
+//  SMEM:   SoA arrays in shared memory (bank group = pair index mod 8, so lanes on different pairs spread over all
+//          banks) in two orderings per axis: (c0.min, c0.max, c1.min, c1.max) for rays travelling up the axis and
+//          (c0.max, c0.min, c1.max, c1.min) for rays travelling down, so that component .x/.z is always the near plane.
+//  global: the 128-B PairRec (both orderings, one L1 line per pair) through ld.global.nc.
+template <bool SMEM>
+struct PairView {
+    const float4 *x, *y, *z;      // SMEM: base of the "up" arrays; the "down" arrays follow at +n_pairs
+    const uint2 *l;
+    const PairRec *g;
+    uint32_t n_pairs;
+    // nx/ny/nz: 1 when the ray travels down that axis (fast path only; the literal path always passes 0)
+    __device__ __forceinline__ void load(uint32_t p, uint32_t nx, uint32_t ny, uint32_t nz, float4 &bx, float4 &by, float4 &bz,
+                                         uint2 &lk) const {
+        if (SMEM) {
+            bx = x[p + nx * n_pairs]; by = y[p + ny * n_pairs]; bz = z[p + nz * n_pairs]; lk = l[p];
+        } else {
+            const float4 *pp = reinterpret_cast<const float4 *>(g + p);
+            bx = __ldg(pp + 4 * nx); by = __ldg(pp + 1 + 4 * ny); bz = __ldg(pp + 2 + 4 * nz);
+            lk = __ldg(reinterpret_cast<const uint2 *>(pp + 3));
+        }
+    }
+};
+
+constexpr uint32_t CUR_END = 0xFFFFFFFFu;   // traversal finished
+
+// One interior visit of intersect_bvh_iterative (shaders.metal:134-154): slab-test both children (:87-95), order them,
+// descend / pop.
+//
+// FAST (guarded ranges, no zero / NaN / inf anywhere): the quotients are the exact RN((b - o)/d) of the literal code and
+// (b_min - o)/d <= (b_max - o)/d holds for d > 0 by monotonicity of rounding (reversed for d < 0), so with the pair
+// loaded in travel order min(t1,t2) is the first and max(t1,t2) the second component: tmin = max3(near), tmax = min3(far).
+// The literal `dist` values are never materialised: with hit_k = (tmax_k >= tmin_k && tmin_k < t && tmax_k > 0) and
+// dist_k = hit_k ? tmin_k : 1e30 (tmin_k < t <= 1e30 when hit), `dist1 > dist2` is hit2 && (!hit1 || tmin1 > tmin2),
+// `dist_near == 1e30` is !hit1 && !hit2 and `dist_far != 1e30` is hit1 && hit2 — the same decisions, fewer instructions.
 template <bool FAST, bool CNT>
-__device__ __forceinline__ void traverse(const Pair *__restrict__ pairs, const RectI *__restrict__ rects, uint32_t root,
-                                         V3 ori, V3 dir, float &beam_t, uint32_t &beam_slot, uint32_t *stack, Tally &tl) {
+__device__ __forceinline__ void inner_step(const float4 &bx, const float4 &by, const float4 &bz, const uint2 &lk, const Axis &ax,
+                                           const Axis &ay, const Axis &az, float t, uint32_t &cur, uint32_t &head, uint32_t *stack,
+                                           Tally &tl) {
+    float lo1, hi1, lo2, hi2;
+    if (FAST) {
+        lo1 = fmaxf(fmaxf(quot<true>(bx.x, ax), quot<true>(by.x, ay)), quot<true>(bz.x, az));
+        hi1 = fminf(fminf(quot<true>(bx.y, ax), quot<true>(by.y, ay)), quot<true>(bz.y, az));
+        lo2 = fmaxf(fmaxf(quot<true>(bx.z, ax), quot<true>(by.z, ay)), quot<true>(bz.z, az));
+        hi2 = fminf(fminf(quot<true>(bx.w, ax), quot<true>(by.w, ay)), quot<true>(bz.w, az));
+    } else {
+        float t1 = quot<false>(bx.x, ax), t2 = quot<false>(bx.y, ax);
+        lo1 = fminf(t1, t2); hi1 = fmaxf(t1, t2);
+        t1 = quot<false>(by.x, ay); t2 = quot<false>(by.y, ay);
+        lo1 = fmaxf(lo1, fminf(t1, t2)); hi1 = fminf(hi1, fmaxf(t1, t2));
+        t1 = quot<false>(bz.x, az); t2 = quot<false>(bz.y, az);
+        lo1 = fmaxf(lo1, fminf(t1, t2)); hi1 = fminf(hi1, fmaxf(t1, t2));
+        t1 = quot<false>(bx.z, ax); t2 = quot<false>(bx.w, ax);
+        lo2 = fminf(t1, t2); hi2 = fmaxf(t1, t2);
+        t1 = quot<false>(by.z, ay); t2 = quot<false>(by.w, ay);
+        lo2 = fmaxf(lo2, fminf(t1, t2)); hi2 = fminf(hi2, fmaxf(t1, t2));
+        t1 = quot<false>(bz.z, az); t2 = quot<false>(bz.w, az);
+        lo2 = fmaxf(lo2, fminf(t1, t2)); hi2 = fminf(hi2, fmaxf(t1, t2));
+    }
+    const bool hit1 = (hi1 >= lo1) & (lo1 < t) & (hi1 > 0.0f);          // :94
+    const bool hit2 = (hi2 >= lo2) & (lo2 < t) & (hi2 > 0.0f);
+    const bool swap = hit2 & (!hit1 | (lo1 > lo2));                     // :140, ties keep the left child first
+    if (!(hit1 | hit2)) {                                               // :149-150
+        cur = head == 0 ? CUR_END : stack[head - 1];
+        head = head == 0 ? 0 : head - 1;
+    } else {                                                            // :151-154
+        cur = swap ? lk.y : lk.x;
+        if (hit1 & hit2) {
+            stack[head++] = swap ? lk.x : lk.y;
+            if (CNT) tl.max_stack = max(tl.max_stack, head);
+        }
+    }
+}
+
+// One leaf visit (shaders.metal:127-129 with ray_rect_intersect :51-67 inlined), then pop / finish.
+template <bool CNT>
+__device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 ori, V3 dir, float &t, uint32_t &slot, uint32_t &cur,
+                                          uint32_t &head, const uint32_t *stack, Tally &tl) {
+    const uint32_t first = cur & 0xFFFFFFu, count = cur >> 24;
+    for (uint32_t i = 0; i < count; i++) {
+        const float4 *rp = reinterpret_cast<const float4 *>(rects + first + i);
+        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
+        if (CNT) tl.rect++;
+        const V3 ro = mk(r0.x, r0.y, r0.z), n = mk(r1.x, r1.y, r1.z), v = mk(r2.x, r2.y, r2.z), u = mk(r3.x, r3.y, r3.z);
+        const float len_v = r0.w, len_u = r1.w;
+        const float norm_check = dot3(dir, n);                                   // :53
+        const float a = fdiv(dot3(sub3(ro, ori), n), norm_check);                // :55
+        const V3 isect = add3(ori, scale3(dir, a));                              // :56
+        const V3 rv = sub3(isect, ro);                                           // :58
+        const float d1 = fdiv(dot3(rv, v), len_v);                               // :60
+        const float d2 = fdiv(dot3(rv, u), len_u);                               // :61
+        if ((0.0f <= d1 && d1 <= len_v) && (0.0f <= d2 && d2 <= len_u) && norm_check != 0.0f && a > 0.1f && a < t) {   // :63
+            t = a;
+            slot = first + i;
+        }
+    }
+    cur = head == 0 ? CUR_END : stack[head - 1];
+    head = head == 0 ? 0 : head - 1;
+}
+
+// intersect_bvh_iterative (shaders.metal:115-156) for one ray.  Lanes of a warp run it together; interior visits are
+// batched (a lane that reaches a leaf waits until every lane has reached a leaf or finished) so that the interior body,
+// 90 % of the kernel's instructions, is not interleaved with the leaf body.
+template <bool FAST, bool SMEM, bool CNT>
+__device__ __forceinline__ void traverse(const PairView<SMEM> &pv, const RectI *__restrict__ rects, uint32_t root, V3 ori, V3 dir,
+                                         float &beam_t, uint32_t &beam_slot, uint32_t *stack, Tally &tl) {
     Axis ax, ay, az;
     ax.o = ori.x; ax.d = dir.x; ay.o = ori.y; ay.d = dir.y; az.o = ori.z; az.d = dir.z;
+    uint32_t nx = 0, ny = 0, nz = 0;
     if (FAST) {
         ax.r = __frcp_rn(ax.d); ax.rl = fmul(__fmaf_rn(-ax.d, ax.r, 1.0f), ax.r);
         ay.r = __frcp_rn(ay.d); ay.rl = fmul(__fmaf_rn(-ay.d, ay.r, 1.0f), ay.r);
         az.r = __frcp_rn(az.d); az.rl = fmul(__fmaf_rn(-az.d, az.r, 1.0f), az.r);
+        nx = ax.d < 0.0f; ny = ay.d < 0.0f; nz = az.d < 0.0f;
     } else {
         ax.r = ax.rl = ay.r = ay.rl = az.r = az.rl = 0.0f;
     }
-    uint32_t cur = root;
-    uint32_t head = 0;
+    uint32_t cur = root, head = 0, slot = beam_slot;
     float t = beam_t;
-    uint32_t slot = beam_slot;
-    while (true) {
-        bool done = false;
+    while (cur != CUR_END) {
         while ((cur >> 24) == 0u) {
-            // interior: slab-test both children (shaders.metal:134-138)
-            const float4 *pp = reinterpret_cast<const float4 *>(pairs + cur);
-            float4 bx = pp[0], by = pp[1], bz = pp[2];
-            uint2 lk = *reinterpret_cast<const uint2 *>(pp + 3);
+            float4 bx, by, bz;
+            uint2 lk;
+            pv.load(cur, nx, ny, nz, bx, by, bz, lk);
             if (CNT) tl.inner++;
-            float dist1, dist2;
-            {
-                float t1 = quot<FAST>(bx.x, ax), t2 = quot<FAST>(bx.y, ax);
-                float tmin = fminf(t1, t2), tmax = fmaxf(t1, t2);
-                t1 = quot<FAST>(by.x, ay); t2 = quot<FAST>(by.y, ay);
-                tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
-                t1 = quot<FAST>(bz.x, az); t2 = quot<FAST>(bz.y, az);
-                tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
-                dist1 = (tmax >= tmin && tmin < t && tmax > 0.0f) ? tmin : 1e30f;
-            }
-            {
-                float t1 = quot<FAST>(bx.z, ax), t2 = quot<FAST>(bx.w, ax);
-                float tmin = fminf(t1, t2), tmax = fmaxf(t1, t2);
-                t1 = quot<FAST>(by.z, ay); t2 = quot<FAST>(by.w, ay);
-                tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
-                t1 = quot<FAST>(bz.z, az); t2 = quot<FAST>(bz.w, az);
-                tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
-                dist2 = (tmax >= tmin && tmin < t && tmax > 0.0f) ? tmin : 1e30f;
-            }
-            uint32_t near_d = lk.x, far_d = lk.y;
-            if (dist1 > dist2) {                                   // :140-148, ties keep the left child first
-                float tmp = dist1; dist1 = dist2; dist2 = tmp;
-                near_d = lk.y; far_d = lk.x;
-            }
-            if (dist1 == 1e30f) {                                  // :149-150
-                if (head == 0) { done = true; break; }
-                cur = stack[--head];
-            } else {                                               // :151-154
-                cur = near_d;
-                if (dist2 != 1e30f) {
-                    stack[head++] = far_d;
-                    if (CNT) tl.max_stack = max(tl.max_stack, head);
-                }
-            }
+            inner_step<FAST, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
         }
-        if (done) break;
-        // leaf: test every rect (shaders.metal:127-129)
-        uint32_t first = cur & 0xFFFFFFu, count = cur >> 24;
+        if (cur == CUR_END) break;
         if (CNT) tl.leaf++;
-        for (uint32_t i = 0; i < count; i++) {
-            const float4 *rp = reinterpret_cast<const float4 *>(rects + first + i);
-            float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3];
-            if (CNT) tl.rect++;
-            V3 ro = mk(r0.x, r0.y, r0.z), n = mk(r1.x, r1.y, r1.z), v = mk(r2.x, r2.y, r2.z), u = mk(r3.x, r3.y, r3.z);
-            float len_v = r0.w, len_u = r1.w;
-            float norm_check = dot3(dir, n);                                   // :53
-            float a = fdiv(dot3(sub3(ro, ori), n), norm_check);                // :55
-            V3 isect = add3(ori, scale3(dir, a));                              // :56
-            V3 rv = sub3(isect, ro);                                           // :58
-            float d1 = fdiv(dot3(rv, v), len_v);                               // :60
-            float d2 = fdiv(dot3(rv, u), len_u);                               // :61
-            if ((0.0f <= d1 && d1 <= len_v) && (0.0f <= d2 && d2 <= len_u) && norm_check != 0.0f && a > 0.1f && a < t) {   // :63
-                t = a;
-                slot = first + i;
-            }
-        }
-        if (head == 0) break;
-        cur = stack[--head];
+        leaf_step<CNT>(rects, ori, dir, t, slot, cur, head, stack, tl);
     }
     beam_t = t;
     beam_slot = slot;
@@ -196,17 +243,32 @@ __device__ __forceinline__ void sample_noise_xy(const uint8_t *noise, uint32_t n
 }
 
 template <bool SMEM_NODES, bool CNT, bool DBG>
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, 2)
 trace_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *red = reinterpret_cast<float *>(smem_raw);                      // 3 * kBlockThreads floats
-    const Pair *pairs = P.pairs;
+    PairView<SMEM_NODES> pv;
+    pv.g = P.pairs;
+    pv.n_pairs = P.n_pairs;
     if (SMEM_NODES) {
-        Pair *sp = reinterpret_cast<Pair *>(smem_raw + 3 * kBlockThreads * sizeof(float));
+        // smem: [x up | x down | y up | y down | z up | z down] float4[n_pairs] each, then links uint2[n_pairs]
+        float4 *sx = reinterpret_cast<float4 *>(smem_raw + 3 * kBlockThreads * sizeof(float));
+        float4 *sy = sx + 2 * P.n_pairs, *sz = sy + 2 * P.n_pairs;
+        uint2 *sl = reinterpret_cast<uint2 *>(sz + 2 * P.n_pairs);
         const float4 *src = reinterpret_cast<const float4 *>(P.pairs);
-        float4 *dst = reinterpret_cast<float4 *>(sp);
-        for (uint32_t i = threadIdx.x; i < P.n_pairs * 4u; i += kBlockThreads) dst[i] = src[i];
-        pairs = sp;
+        for (uint32_t i = threadIdx.x; i < P.n_pairs * 8u; i += kBlockThreads) {
+            const uint32_t pr = i >> 3, c = i & 7u;
+            if (c == 7u) continue;
+            const float4 v = src[i];
+            if (c == 0) sx[pr] = v;
+            else if (c == 1) sy[pr] = v;
+            else if (c == 2) sz[pr] = v;
+            else if (c == 3) sl[pr] = make_uint2(__float_as_uint(v.x), __float_as_uint(v.y));
+            else if (c == 4) sx[pr + P.n_pairs] = v;
+            else if (c == 5) sy[pr + P.n_pairs] = v;
+            else sz[pr + P.n_pairs] = v;
+        }
+        pv.x = sx; pv.y = sy; pv.z = sz; pv.l = sl;
         __syncthreads();
     }
 
@@ -217,6 +279,7 @@ trace_kernel(const __grid_constant__ KParams P) {
     uint32_t seg = 0, nhits = 0, nliteral = 0;
     V3 sample = mk(0.0f, 0.0f, 0.0f);
     uint32_t pxx = 0, pxy = 0, k = 0, flat = 0;
+    const uint32_t root = P.root_link | (P.root_count << 24);
 
     if (active) {
         k = (uint32_t)(path / P.T);
@@ -259,22 +322,22 @@ trace_kernel(const __grid_constant__ KParams P) {
             const bool fast = !P.force_literal && P.scene_fast_ok && axis_safe(ori.x, dir.x) && axis_safe(ori.y, dir.y) &&
                               axis_safe(ori.z, dir.z);
             if (fast) {
-                traverse<true, CNT>(pairs, P.rects, P.root_link | (P.root_count << 24), ori, dir, t, slot, stack, tl);
+                traverse<true, SMEM_NODES, CNT>(pv, P.rects, root, ori, dir, t, slot, stack, tl);
             } else {
-                traverse<false, CNT>(pairs, P.rects, P.root_link | (P.root_count << 24), ori, dir, t, slot, stack, tl);
+                traverse<false, SMEM_NODES, CNT>(pv, P.rects, root, ori, dir, t, slot, stack, tl);
                 nliteral++;
             }
             seg++;
             if (!(t < 1e30f)) break;                                       // :308, :336-339 (sky term is * 0.0)
             nhits++;
             const float4 *rp = reinterpret_cast<const float4 *>(P.rects + slot);
-            const float4 r1 = rp[1], r2 = rp[2], r3 = rp[3];
+            const float4 r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
             if (DBG && n == 0) first_hit = __float_as_uint(r2.w);
-            const V3 nrm = mk(r1.x, r1.y, r1.z);                           // :309 (precomputed, same operations)
+            const V3 nrm = mk(r1.x, r1.y, r1.z);                           // :309 (per-rect constant, same operations)
             const float side = -sign1(dot3(dir, nrm));                     // :310
             const float4 *sp4 = reinterpret_cast<const float4 *>(P.shade + slot);
             if (__float_as_uint(r3.w) == 0u || side == -1.0f) {            // :311
-                const float4 col = sp4[0], emi = sp4[1];
+                const float4 col = __ldg(sp4), emi = __ldg(sp4 + 1);
                 light = add3(light, mul3(mk(emi.x, emi.y, emi.z), color)); // :312-313
                 color = mul3(color, mk(col.x, col.y, col.z));              // :314
                 V3 rd;
@@ -289,7 +352,7 @@ trace_kernel(const __grid_constant__ KParams P) {
             } else {
                 mirror_hits++;                                             // :325
                 if (mirror_hits < P.mirror_limit) {                        // :326
-                    const float4 col = sp4[0];
+                    const float4 col = __ldg(sp4);
                     light = add3(light, scale3(mk(col.x, col.y, col.z), 0.005f));   // :327
                     ori = add3(ori, scale3(dir, t));                       // :328
                     dir = normalize3(reflect3(dir, nrm));                  // :329

@@ -6,17 +6,22 @@
 
 namespace mmk {
 
-// One interior node's two children, 64 B, 64-B aligned (one 128-B line holds two pairs).
-// The reference node array (32 B each, children adjacent but only 32-B aligned; shaders.metal:30-35,134-135) is
-// re-laid per inner node so that one traversal step is four 16-B loads, one per slab axis plus the links:
-//   x = (c0.min.x, c0.max.x, c1.min.x, c1.max.x)   y, z likewise
-//   link = (c0.link, c0.count, c1.link, c1.count); count > 0: leaf, link = first slot in the leaf-ordered rect
-//   array; count == 0: interior, link = pair index of that child.
-struct __align__(16) Pair {
+// One interior node's two children, 128 B = one L1/L2 line.
+// The reference node array (32 B each, children adjacent; shaders.metal:30-35,134-135) is re-laid per inner node so that
+// one traversal step is three 16-B loads (one per slab axis) plus an 8-B link load, and stored in both travel orders:
+//   up   : x = (c0.min.x, c0.max.x, c1.min.x, c1.max.x)   for rays with dir.x > 0  (near plane first)
+//   down : x = (c0.max.x, c0.min.x, c1.max.x, c1.min.x)   for rays with dir.x < 0
+//   y, z likewise;  link = (c0.desc, c1.desc, 0, 0) with desc = link | count << 24: count > 0 is a leaf whose link is the
+//   first slot in the leaf-ordered rect array, count == 0 an interior node whose link is its pair index.
+// The kernel's shared-memory copy is SoA over pairs (see PairView in render_kernel.cu).
+struct __align__(16) PairRec {
     float4 x, y, z;
     uint4 link;
+    float4 xd, yd, zd;
+    uint4 pad;
 };
-static_assert(sizeof(Pair) == 64, "pair is 64 B");
+static_assert(sizeof(PairRec) == 128, "pair record is 128 B");
+constexpr uint32_t kPairSmemBytes = 6 * 16 + 8;   // bytes of shared memory per pair (six float4 + one uint2)
 
 // One rectangle in leaf order (slot s = position in the reference `indices` array), 64 B.
 // The normal and the edge lengths are per-rect constants of ray_rect_intersect (shaders.metal:52,60-61); they are
@@ -53,9 +58,11 @@ struct KParams {
     uint32_t root_link, root_count;   // descriptor of node 0 (pair 0 unless the root is a leaf)
     uint32_t noise_w, noise_h;
     uint32_t force_literal;
+    uint32_t th_inner, w_inner, w_leaf, w_shade;   // warp scheduler: run the interior body when >= th_inner lanes want it, else the
+                                                   // body with the largest weighted lane count
     uint32_t scene_fast_ok;
     uint64_t total_paths;
-    const Pair *pairs;
+    const PairRec *pairs;
     const RectI *rects;
     const RectS *shade;
     const mm_chunk *chunks;
@@ -67,7 +74,7 @@ struct KParams {
     float *dbg_radiance;
 };
 
-constexpr int kBlockThreads = 256;
+constexpr int kBlockThreads = 512;   // 2 blocks/SM at <= 64 registers: 32 warps/SM, shared-memory scene copy amortised over 16 warps
 
 // Returns the kernel's static properties for the occupancy query and launch.
 struct KernelChoice { bool smem_nodes, counters, debug; };

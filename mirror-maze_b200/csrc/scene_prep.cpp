@@ -46,19 +46,24 @@ int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *
         const mm_bvh_node &nd = nodes[c];
         return nd.tri_count > 0 ? (nd.left_first | (nd.tri_count << 24)) : pair_id[c];
     };
-    out.pairs.assign(n_pairs ? n_pairs : 1, Pair());
-    std::memset(out.pairs.data(), 0, out.pairs.size() * sizeof(Pair));
+    out.pairs.assign(n_pairs ? n_pairs : 1, PairRec());
+    std::memset(out.pairs.data(), 0, out.pairs.size() * sizeof(PairRec));
     bool fast_ok = true;
     for (uint32_t i = 0; i < n_nodes; i++) {
         if (nodes[i].tri_count != 0) continue;
         const mm_bvh_node &a = nodes[nodes[i].left_first], &b = nodes[nodes[i].left_first + 1];
-        Pair &p = out.pairs[pair_id[i]];
+        PairRec &p = out.pairs[pair_id[i]];
         p.x = make_float4(a.aabb_min.x, a.aabb_max.x, b.aabb_min.x, b.aabb_max.x);
         p.y = make_float4(a.aabb_min.y, a.aabb_max.y, b.aabb_min.y, b.aabb_max.y);
         p.z = make_float4(a.aabb_min.z, a.aabb_max.z, b.aabb_min.z, b.aabb_max.z);
+        p.xd = make_float4(p.x.y, p.x.x, p.x.w, p.x.z);
+        p.yd = make_float4(p.y.y, p.y.x, p.y.w, p.y.z);
+        p.zd = make_float4(p.z.y, p.z.x, p.z.w, p.z.z);
         p.link = make_uint4(desc(nodes[i].left_first), desc(nodes[i].left_first + 1), 0u, 0u);
         const float *c = &p.x.x;
         for (int k = 0; k < 12; k++) fast_ok = fast_ok && coord_ok(c[k]);
+        // the travel-ordered fast path also needs min <= max on every axis (true for every box the builder emits)
+        fast_ok = fast_ok && p.x.x <= p.x.y && p.x.z <= p.x.w && p.y.x <= p.y.y && p.y.z <= p.y.w && p.z.x <= p.z.y && p.z.z <= p.z.w;
     }
     out.n_pairs = n_pairs;
     out.root_link = nodes[0].tri_count > 0 ? nodes[0].left_first : 0u;

@@ -8,7 +8,7 @@
 namespace mmk {
 
 struct Prepared {
-    std::vector<Pair> pairs;
+    std::vector<PairRec> pairs;
     std::vector<RectI> rects;
     std::vector<RectS> shade;
     uint32_t n_pairs = 0, root_link = 0, root_count = 0, depth = 0, max_leaf = 0;

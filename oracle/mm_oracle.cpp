@@ -68,7 +68,10 @@ struct Scene {
     const mm_float4 *emissions;
 };
 
-struct Counts { uint64_t rays = 0, inner = 0, leaf = 0, rect = 0, hits = 0, max_stack = 0; bool overflow = false; };
+struct Counts {
+    uint64_t rays = 0, inner = 0, leaf = 0, rect = 0, hits = 0, max_stack = 0; bool overflow = false;
+    std::vector<uint16_t> *trace = nullptr;   // optional event trace for scheduling studies (tools/sched_sim.py)
+};
 
 // shaders.metal:181-186
 inline float random_f(uint32_t &state) {
@@ -126,11 +129,13 @@ inline void intersect_bvh_iterative(Ray &beam, const Scene &sc, Counts &c) {
     uint32_t node = 0;                // &nodes[0]; the root box is never tested
     uint32_t stack[50];
     uint32_t head = 0;
+    uint32_t run = 0;
     c.rays++;
     while (true) {
         const mm_bvh_node &nd = sc.nodes[node];
         if (nd.tri_count > 0) {
             c.leaf++;
+            if (c.trace) { c.trace->push_back((uint16_t)run); c.trace->push_back((uint16_t)nd.tri_count); run = 0; }
             for (uint32_t i = 0; i < nd.tri_count; i++) {
                 uint32_t pi = sc.indices[nd.left_first + i];
                 ray_rect_intersect(beam, sc.rects[pi], pi);
@@ -140,6 +145,7 @@ inline void intersect_bvh_iterative(Ray &beam, const Scene &sc, Counts &c) {
             continue;
         }
         c.inner++;
+        run++;
         uint32_t left = nd.left_first, right = nd.left_first + 1;
         float dist1 = intersect_aabb(beam, ld(sc.nodes[left].aabb_min), ld(sc.nodes[left].aabb_max));
         float dist2 = intersect_aabb(beam, ld(sc.nodes[right].aabb_min), ld(sc.nodes[right].aabb_max));
@@ -158,6 +164,7 @@ inline void intersect_bvh_iterative(Ray &beam, const Scene &sc, Counts &c) {
             }
         }
     }
+    if (c.trace) { c.trace->push_back((uint16_t)run); c.trace->push_back(0xFFFFu); }   // trailing interior run, end of segment
 }
 
 struct Job {
@@ -270,6 +277,7 @@ inline f3 trace_thread(const Job &j, uint32_t tgx, uint32_t tgy, uint32_t flat, 
             break;   // :337-338: the sky term is multiplied by 0.0 — adds nothing
         }
     }
+    if (c.trace) c.trace->push_back(0xFFFEu);   // end of path
     if (first_hit) *first_hit = fh;
     if (segments) *segments = seg;
     if (mirror_out) *mirror_out = (uint32_t)mirror_hits;
@@ -371,6 +379,33 @@ int mmo_render(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *nod
         counters->max_stack = total.max_stack;
     }
     return overflow ? MM_ERR_BVH : MM_OK;
+}
+
+// Event trace of a render (single-threaded): per path, per segment, (interior-run, leaf-count) pairs, 0xFFFF after the
+// trailing interior run of a segment, 0xFFFE after a path.  Returns the number of u16 written (or needed if cap is small).
+uint64_t mmo_trace(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *nodes, uint32_t n_nodes, const uint32_t *indices,
+                   const uint8_t *materials, const mm_float4 *emissions, const uint8_t *noise_rgba8, uint32_t noise_w, uint32_t noise_h,
+                   const mm_uniform *uni, const mm_params *params, const mm_chunk *chunks, uint32_t n_chunks, uint16_t *out, uint64_t cap) {
+    uint32_t T = 0;
+    if (validate(uni, params, n_chunks, &T) != MM_OK) return 0;
+    Job j;
+    j.sc = {planes, n_planes, nodes, n_nodes, indices, materials, emissions};
+    j.noise = noise_rgba8; j.nw = noise_w; j.nh = noise_h;
+    j.uni = *uni; j.par = *params; j.chunks = chunks; j.n_chunks = n_chunks;
+    uint32_t first = params->group_first, step = params->group_step ? params->group_step : 1, count = params->group_count;
+    if (count == 0) { first = 0; step = 1; count = params->grid_x * params->grid_y; }
+    const uint32_t dimx = T < 32 ? T : 32, dimy = T / dimx;
+    std::vector<uint16_t> tr;
+    Counts c;
+    c.trace = &tr;
+    uint32_t pix[2];
+    for (uint32_t k = 0; k < count; k++) {
+        uint32_t g = first + k * step;
+        for (uint32_t flat = 0; flat < T; flat++)
+            trace_thread(j, g % params->grid_x, g / params->grid_x, flat, dimx, dimy, c, nullptr, nullptr, nullptr, nullptr, pix);
+    }
+    if (out && tr.size() <= cap) std::memcpy(out, tr.data(), tr.size() * sizeof(uint16_t));
+    return tr.size();
 }
 
 // Unit-level entry points for known-answer tests.
