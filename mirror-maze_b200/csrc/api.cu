@@ -59,12 +59,13 @@ static int fail(mm_ctx *ctx, int code, const std::string &msg) {
     return code;
 }
 
-static size_t smem_nodes_limit() {
-    // Child pairs are staged in shared memory when they fit beside the reduction scratch with at least two
-    // resident blocks per SM; larger trees are read through L1 (ld.global.nc).  MM_SMEM_NODE_LIMIT overrides (bytes).
+static size_t smem_nodes_limit(bool forced) {
+    // Child pairs are read through L1 (ld.global.nc, one 128-B line per pair) by default: measured on B200 it beats a
+    // per-block shared-memory copy (48.9 vs 50.5 ms on the 32x32-maze frame, profiles/r1_sched_sweep.txt).  The
+    // shared-memory variant is kept behind MM_FLAG_FORCE_SHARED / MM_SMEM_NODE_LIMIT (bytes) for trees that fit twice per SM.
     const char *e = getenv("MM_SMEM_NODE_LIMIT");
     if (e) return (size_t)strtoull(e, nullptr, 10);
-    return 105 * 1024;
+    return forced ? 105 * 1024 : 0;
 }
 
 extern "C" {
@@ -228,7 +229,7 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
     p.noise_w = ctx->noise_w; p.noise_h = ctx->noise_h;
     p.force_literal = (par->flags & MM_FLAG_FORCE_LITERAL) ? 1u : 0u;
     p.scene_fast_ok = ctx->fast_ok ? 1u : 0u;
-    p.th_inner = 16; p.w_inner = 1; p.w_leaf = 1; p.w_shade = 1;
+    p.th_inner = 16; p.w_inner = 1; p.w_leaf = 3; p.w_shade = 1;   // measured best on B200 (profiles/r1_sched_sweep.txt)
     if (const char *e = getenv("MM_SCHED")) {   // tuning hook: "th,wI,wL,wS"
         unsigned a, b, c, d;
         if (sscanf(e, "%u,%u,%u,%u", &a, &b, &c, &d) == 4 && a >= 1 && b >= 1 && c >= 1 && d >= 1) {   // th = 0 would never leave the loop
@@ -242,7 +243,7 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
 
     const size_t red_bytes = 3 * kBlockThreads * sizeof(float);
     const size_t pair_bytes = (size_t)ctx->n_pairs * kPairSmemBytes;
-    bool smem_nodes = ctx->n_pairs > 0 && !(par->flags & MM_FLAG_FORCE_GLOBAL) && pair_bytes <= smem_nodes_limit() &&
+    bool smem_nodes = ctx->n_pairs > 0 && !(par->flags & MM_FLAG_FORCE_GLOBAL) && pair_bytes <= smem_nodes_limit((par->flags & MM_FLAG_FORCE_SHARED) != 0) &&
                       red_bytes + pair_bytes <= ctx->smem_optin;
     L.choice.smem_nodes = smem_nodes;
     L.choice.debug = debug;

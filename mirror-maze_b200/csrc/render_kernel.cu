@@ -195,12 +195,16 @@ __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 or
     head = head == 0 ? 0 : head - 1;
 }
 
-// intersect_bvh_iterative (shaders.metal:115-156) for one ray.  Lanes of a warp run it together; interior visits are
-// batched (a lane that reaches a leaf waits until every lane has reached a leaf or finished) so that the interior body,
-// 90 % of the kernel's instructions, is not interleaved with the leaf body.
+// intersect_bvh_iterative (shaders.metal:115-156) for one ray.  The lanes of a warp run their rays together and vote,
+// every step, on which body to execute: the interior body runs while the lanes standing at an interior node outweigh
+// the lanes waiting at a leaf (w_inner * nI >= w_leaf * nL), otherwise the waiting lanes test their rects.  Each lane
+// still performs exactly the reference's sequence of visits for its own ray; only the interleaving between lanes
+// changes.  (A plain while-while loop — all lanes descend to a leaf, then all test — left 12 of 32 lanes active in the
+// interior body; see profiles/.)
 template <bool FAST, bool SMEM, bool CNT>
 __device__ __forceinline__ void traverse(const PairView<SMEM> &pv, const RectI *__restrict__ rects, uint32_t root, V3 ori, V3 dir,
-                                         float &beam_t, uint32_t &beam_slot, uint32_t *stack, Tally &tl) {
+                                         float &beam_t, uint32_t &beam_slot, uint32_t *stack, Tally &tl, uint32_t w_inner,
+                                         uint32_t w_leaf) {
     Axis ax, ay, az;
     ax.o = ori.x; ax.d = dir.x; ay.o = ori.y; ay.d = dir.y; az.o = ori.z; az.d = dir.z;
     uint32_t nx = 0, ny = 0, nz = 0;
@@ -214,17 +218,26 @@ __device__ __forceinline__ void traverse(const PairView<SMEM> &pv, const RectI *
     }
     uint32_t cur = root, head = 0, slot = beam_slot;
     float t = beam_t;
-    while (cur != CUR_END) {
-        while ((cur >> 24) == 0u) {
-            float4 bx, by, bz;
-            uint2 lk;
-            pv.load(cur, nx, ny, nz, bx, by, bz, lk);
-            if (CNT) tl.inner++;
-            inner_step<FAST, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
+    const unsigned peers = __activemask();       // the lanes that entered this instantiation together
+    while (true) {
+        const bool isI = (cur >> 24) == 0u;
+        const bool isL = !isI && cur != CUR_END;
+        const unsigned mI = __ballot_sync(peers, isI), mL = __ballot_sync(peers, isL);
+        if ((mI | mL) == 0u) break;
+        if (mI != 0u && __popc(mI) * w_inner >= __popc(mL) * w_leaf) {
+            if (isI) {
+                float4 bx, by, bz;
+                uint2 lk;
+                pv.load(cur, nx, ny, nz, bx, by, bz, lk);
+                if (CNT) tl.inner++;
+                inner_step<FAST, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
+            }
+        } else {
+            if (isL) {
+                if (CNT) tl.leaf++;
+                leaf_step<CNT>(rects, ori, dir, t, slot, cur, head, stack, tl);
+            }
         }
-        if (cur == CUR_END) break;
-        if (CNT) tl.leaf++;
-        leaf_step<CNT>(rects, ori, dir, t, slot, cur, head, stack, tl);
     }
     beam_t = t;
     beam_slot = slot;
@@ -322,9 +335,9 @@ trace_kernel(const __grid_constant__ KParams P) {
             const bool fast = !P.force_literal && P.scene_fast_ok && axis_safe(ori.x, dir.x) && axis_safe(ori.y, dir.y) &&
                               axis_safe(ori.z, dir.z);
             if (fast) {
-                traverse<true, SMEM_NODES, CNT>(pv, P.rects, root, ori, dir, t, slot, stack, tl);
+                traverse<true, SMEM_NODES, CNT>(pv, P.rects, root, ori, dir, t, slot, stack, tl, P.w_inner, P.w_leaf);
             } else {
-                traverse<false, SMEM_NODES, CNT>(pv, P.rects, root, ori, dir, t, slot, stack, tl);
+                traverse<false, SMEM_NODES, CNT>(pv, P.rects, root, ori, dir, t, slot, stack, tl, P.w_inner, P.w_leaf);
                 nliteral++;
             }
             seg++;
