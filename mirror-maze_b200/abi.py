@@ -153,7 +153,7 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    path = library_path()
+    path = os.environ.get("MM_LIBRARY") or library_path()      # MM_LIBRARY: developer override for A/B builds
     if not os.path.exists(path):
         raise MMError(-2, f"{path} is missing: build it with `make -C {_HERE}` (or __graft_entry__.build()); "
                           "there is no CPU fallback for the render path")

@@ -195,42 +195,40 @@ __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 or
     head = head == 0 ? 0 : head - 1;
 }
 
-// intersect_bvh_iterative (shaders.metal:115-156) for one ray.  The lanes of a warp run their rays together and vote,
-// every step, on which body to execute: the interior body runs while the lanes standing at an interior node outweigh
-// the lanes waiting at a leaf (w_inner * nI >= w_leaf * nL), otherwise the waiting lanes test their rects.  Each lane
-// still performs exactly the reference's sequence of visits for its own ray; only the interleaving between lanes
-// changes.  (A plain while-while loop — all lanes descend to a leaf, then all test — left 12 of 32 lanes active in the
-// interior body; see profiles/.)
-template <bool FAST, bool SMEM, bool CNT>
-__device__ __forceinline__ void traverse(const PairView<SMEM> &pv, const RectI *__restrict__ rects, uint32_t root, V3 ori, V3 dir,
-                                         float &beam_t, uint32_t &beam_slot, uint32_t *stack, Tally &tl, uint32_t w_inner,
-                                         uint32_t w_leaf) {
+// intersect_bvh_iterative (shaders.metal:115-156) for the rays of one warp.  Every lane of the warp calls this together
+// (lanes without a ray pass alive = false) and the warp votes, every step, on which body to execute: the interior body
+// runs while the lanes standing at an interior node outweigh the lanes waiting at a leaf (nI >= kLeafWeight * nL),
+// otherwise the waiting lanes test their rects.  Each lane still performs exactly the reference's sequence of visits
+// for its own ray; only the interleaving between lanes changes.  (A plain while-while loop — all lanes descend to a
+// leaf, then all test — left 12 of 32 lanes active in the interior body; see profiles/.)
+// `lit` lanes (operands outside the guarded ranges, or MM_FLAG_FORCE_LITERAL) use the literal-divide slab test.
+constexpr uint32_t kLeafWeight = 3;   // measured best on B200 (profiles/r1_sched_sweep.txt)
+
+// MIXED = false: no lane of the warp is literal (the common case; the loop then contains no literal-divide code).
+template <bool MIXED, bool SMEM, bool CNT>
+__device__ __forceinline__ void traverse(const PairView<SMEM> &pv, const RectI *__restrict__ rects, uint32_t root, bool alive, bool lit,
+                                         V3 ori, V3 dir, float &beam_t, uint32_t &beam_slot, uint32_t *stack, Tally &tl) {
     Axis ax, ay, az;
     ax.o = ori.x; ax.d = dir.x; ay.o = ori.y; ay.d = dir.y; az.o = ori.z; az.d = dir.z;
-    uint32_t nx = 0, ny = 0, nz = 0;
-    if (FAST) {
-        ax.r = __frcp_rn(ax.d); ax.rl = fmul(__fmaf_rn(-ax.d, ax.r, 1.0f), ax.r);
-        ay.r = __frcp_rn(ay.d); ay.rl = fmul(__fmaf_rn(-ay.d, ay.r, 1.0f), ay.r);
-        az.r = __frcp_rn(az.d); az.rl = fmul(__fmaf_rn(-az.d, az.r, 1.0f), az.r);
-        nx = ax.d < 0.0f; ny = ay.d < 0.0f; nz = az.d < 0.0f;
-    } else {
-        ax.r = ax.rl = ay.r = ay.rl = az.r = az.rl = 0.0f;
-    }
-    uint32_t cur = root, head = 0, slot = beam_slot;
+    ax.r = __frcp_rn(ax.d); ax.rl = fmul(__fmaf_rn(-ax.d, ax.r, 1.0f), ax.r);
+    ay.r = __frcp_rn(ay.d); ay.rl = fmul(__fmaf_rn(-ay.d, ay.r, 1.0f), ay.r);
+    az.r = __frcp_rn(az.d); az.rl = fmul(__fmaf_rn(-az.d, az.r, 1.0f), az.r);
+    const uint32_t nx = (!lit && ax.d < 0.0f) ? 1u : 0u, ny = (!lit && ay.d < 0.0f) ? 1u : 0u, nz = (!lit && az.d < 0.0f) ? 1u : 0u;
+    uint32_t cur = alive ? root : CUR_END, head = 0, slot = beam_slot;
     float t = beam_t;
-    const unsigned peers = __activemask();       // the lanes that entered this instantiation together
     while (true) {
         const bool isI = (cur >> 24) == 0u;
         const bool isL = !isI && cur != CUR_END;
-        const unsigned mI = __ballot_sync(peers, isI), mL = __ballot_sync(peers, isL);
+        const unsigned mI = __ballot_sync(0xFFFFFFFFu, isI), mL = __ballot_sync(0xFFFFFFFFu, isL);
         if ((mI | mL) == 0u) break;
-        if (mI != 0u && __popc(mI) * w_inner >= __popc(mL) * w_leaf) {
+        if (mI != 0u && __popc(mI) >= kLeafWeight * __popc(mL)) {
             if (isI) {
                 float4 bx, by, bz;
                 uint2 lk;
                 pv.load(cur, nx, ny, nz, bx, by, bz, lk);
                 if (CNT) tl.inner++;
-                inner_step<FAST, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
+                if (!MIXED || !lit) inner_step<true, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
+                else inner_step<false, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
             }
         } else {
             if (isL) {
@@ -256,7 +254,7 @@ __device__ __forceinline__ void sample_noise_xy(const uint8_t *noise, uint32_t n
 }
 
 template <bool SMEM_NODES, bool CNT, bool DBG>
-__global__ void __launch_bounds__(kBlockThreads, 2)
+__global__ void __launch_bounds__(kBlockThreads, MM_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *red = reinterpret_cast<float *>(smem_raw);                      // 3 * kBlockThreads floats
@@ -293,6 +291,11 @@ trace_kernel(const __grid_constant__ KParams P) {
     V3 sample = mk(0.0f, 0.0f, 0.0f);
     uint32_t pxx = 0, pxy = 0, k = 0, flat = 0;
     const uint32_t root = P.root_link | (P.root_count << 24);
+    V3 st_ori = mk(0.0f, 0.0f, 0.0f), st_dir = mk(1.0f, 1.0f, 1.0f), st_color = mk(1.0f, 1.0f, 1.0f), st_light = mk(0.0f, 0.0f, 0.0f);
+    float st_t = 1e30f;
+    uint32_t st_slot = 0xFFFFFFFFu, st_state = 0u, first_hit = 0xFFFFFFFFu;
+    int mirror_hits = 0;
+    bool n_alive = false;
 
     if (active) {
         k = (uint32_t)(path / P.T);
@@ -328,55 +331,69 @@ trace_kernel(const __grid_constant__ KParams P) {
         float t = 1e30f;
         uint32_t slot = 0xFFFFFFFFu;
         V3 color = mk(1.0f, 1.0f, 1.0f), light = mk(0.0f, 0.0f, 0.0f);
-        int mirror_hits = 0;
-        uint32_t first_hit = 0xFFFFFFFFu;
 
-        for (int n = 0; n < P.bounce_limit + mirror_hits; n++) {           // :306
-            const bool fast = !P.force_literal && P.scene_fast_ok && axis_safe(ori.x, dir.x) && axis_safe(ori.y, dir.y) &&
-                              axis_safe(ori.z, dir.z);
-            if (fast) {
-                traverse<true, SMEM_NODES, CNT>(pv, P.rects, root, ori, dir, t, slot, stack, tl, P.w_inner, P.w_leaf);
-            } else {
-                traverse<false, SMEM_NODES, CNT>(pv, P.rects, root, ori, dir, t, slot, stack, tl, P.w_inner, P.w_leaf);
-                nliteral++;
-            }
-            seg++;
-            if (!(t < 1e30f)) break;                                       // :308, :336-339 (sky term is * 0.0)
-            nhits++;
-            const float4 *rp = reinterpret_cast<const float4 *>(P.rects + slot);
-            const float4 r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
-            if (DBG && n == 0) first_hit = __float_as_uint(r2.w);
-            const V3 nrm = mk(r1.x, r1.y, r1.z);                           // :309 (per-rect constant, same operations)
-            const float side = -sign1(dot3(dir, nrm));                     // :310
-            const float4 *sp4 = reinterpret_cast<const float4 *>(P.shade + slot);
-            if (__float_as_uint(r3.w) == 0u || side == -1.0f) {            // :311
-                const float4 col = __ldg(sp4), emi = __ldg(sp4 + 1);
-                light = add3(light, mul3(mk(emi.x, emi.y, emi.z), color)); // :312-313
-                color = mul3(color, mk(col.x, col.y, col.z));              // :314
-                V3 rd;
-                do {                                                       // :315-318
-                    float a = rnd_pm1(state), b = rnd_pm1(state), c = rnd_pm1(state);
-                    rd = mk(a, b, c);
-                } while (length3(rd) > 1.0f);
-                rd = normalize3(rd);                                       // :319
-                ori = add3(ori, scale3(dir, t));                           // :320
-                dir = normalize3(add3(rd, scale3(nrm, side)));             // :321
-                t = 1e30f;                                                 // :323
-            } else {
-                mirror_hits++;                                             // :325
-                if (mirror_hits < P.mirror_limit) {                        // :326
-                    const float4 col = __ldg(sp4);
-                    light = add3(light, scale3(mk(col.x, col.y, col.z), 0.005f));   // :327
-                    ori = add3(ori, scale3(dir, t));                       // :328
-                    dir = normalize3(reflect3(dir, nrm));                  // :329
-                    t = 1e30f;                                             // :330
+        n_alive = 0 < P.bounce_limit;                                      // :306, n = 0
+        st_ori = ori; st_dir = dir; st_t = t; st_slot = slot; st_color = color; st_light = light; st_state = state;
+    }
+
+    // Bounce loop (shaders.metal:306-340).  The lanes of a warp go through it together, segment by segment, so that the
+    // traversal's votes can use the full warp; a lane whose path has ended (or that has no path) idles with alive = false.
+    {
+        V3 ori = st_ori, dir = st_dir, color = st_color, light = st_light;
+        float t = st_t;
+        uint32_t slot = st_slot, state = st_state;
+        int n = 0;
+        bool alive = active && n_alive;
+        while (__any_sync(0xFFFFFFFFu, alive)) {
+            const bool lit = P.force_literal || !P.scene_fast_ok ||
+                             !(axis_safe(ori.x, dir.x) && axis_safe(ori.y, dir.y) && axis_safe(ori.z, dir.z));
+            if (!__any_sync(0xFFFFFFFFu, alive && lit)) traverse<false, SMEM_NODES, CNT>(pv, P.rects, root, alive, false, ori, dir, t, slot, stack, tl);
+            else traverse<true, SMEM_NODES, CNT>(pv, P.rects, root, alive, lit, ori, dir, t, slot, stack, tl);
+            if (alive) {
+                if (lit) nliteral++;
+                seg++;
+                if (!(t < 1e30f)) {                                        // :308, :336-339 (sky term is * 0.0)
+                    alive = false;
                 } else {
-                    break;                                                 // :333
+                    nhits++;
+                    const float4 *rp = reinterpret_cast<const float4 *>(P.rects + slot);
+                    const float4 r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
+                    if (DBG && n == 0) first_hit = __float_as_uint(r2.w);
+                    const V3 nrm = mk(r1.x, r1.y, r1.z);                   // :309 (per-rect constant, same operations)
+                    const float side = -sign1(dot3(dir, nrm));             // :310
+                    const float4 *sp4 = reinterpret_cast<const float4 *>(P.shade + slot);
+                    if (__float_as_uint(r3.w) == 0u || side == -1.0f) {    // :311
+                        const float4 col = __ldg(sp4), emi = __ldg(sp4 + 1);
+                        light = add3(light, mul3(mk(emi.x, emi.y, emi.z), color));   // :312-313
+                        color = mul3(color, mk(col.x, col.y, col.z));      // :314
+                        V3 rd;
+                        do {                                               // :315-318
+                            const float a = rnd_pm1(state), b = rnd_pm1(state), c = rnd_pm1(state);
+                            rd = mk(a, b, c);
+                        } while (length3(rd) > 1.0f);
+                        rd = normalize3(rd);                               // :319
+                        ori = add3(ori, scale3(dir, t));                   // :320
+                        dir = normalize3(add3(rd, scale3(nrm, side)));     // :321
+                        t = 1e30f;                                         // :323
+                    } else {
+                        mirror_hits++;                                     // :325
+                        if (mirror_hits < P.mirror_limit) {                // :326
+                            const float4 col = __ldg(sp4);
+                            light = add3(light, scale3(mk(col.x, col.y, col.z), 0.005f));   // :327
+                            ori = add3(ori, scale3(dir, t));               // :328
+                            dir = normalize3(reflect3(dir, nrm));          // :329
+                            t = 1e30f;                                     // :330
+                        } else {
+                            alive = false;                                 // :333
+                        }
+                    }
+                    n++;
+                    alive = alive && (n < P.bounce_limit + mirror_hits);   // :306
                 }
             }
         }
         sample = mk(fsqrt(fmaxf(light.x, 0.0f)), fsqrt(fmaxf(light.y, 0.0f)), fsqrt(fmaxf(light.z, 0.0f)));   // :344
-        if (DBG) {
+        if (DBG && active) {
             if (P.dbg_first_hit) P.dbg_first_hit[path] = first_hit;
             if (P.dbg_segments) P.dbg_segments[path] = seg;
             if (P.dbg_mirror_hits) P.dbg_mirror_hits[path] = (uint32_t)mirror_hits;

@@ -74,7 +74,13 @@ struct KParams {
     float *dbg_radiance;
 };
 
-constexpr int kBlockThreads = 512;   // 2 blocks/SM at <= 64 registers: 32 warps/SM, shared-memory scene copy amortised over 16 warps
+#ifndef MM_BLOCK_THREADS
+#define MM_BLOCK_THREADS 512
+#endif
+#ifndef MM_MIN_BLOCKS
+#define MM_MIN_BLOCKS 2
+#endif
+constexpr int kBlockThreads = MM_BLOCK_THREADS;   // 32 warps/SM at <= 64 registers (measured best; profiles/r1_block_shape.txt)
 
 // Returns the kernel's static properties for the occupancy query and launch.
 struct KernelChoice { bool smem_nodes, counters, debug; };

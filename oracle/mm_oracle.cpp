@@ -131,6 +131,7 @@ inline void intersect_bvh_iterative(Ray &beam, const Scene &sc, Counts &c) {
     uint32_t head = 0;
     uint32_t run = 0;
     c.rays++;
+    if (c.trace) c.trace->push_back((uint16_t)(0xFFF0u | (beam.dir.x < 0.0f ? 1u : 0u) | (beam.dir.y < 0.0f ? 2u : 0u) | (beam.dir.z < 0.0f ? 4u : 0u)));
     while (true) {
         const mm_bvh_node &nd = sc.nodes[node];
         if (nd.tri_count > 0) {
@@ -381,7 +382,7 @@ int mmo_render(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *nod
     return overflow ? MM_ERR_BVH : MM_OK;
 }
 
-// Event trace of a render (single-threaded): per path, per segment, (interior-run, leaf-count) pairs, 0xFFFF after the
+// Event trace of a render (single-threaded): per path, per segment, 0xFFF0|octant then (interior-run, leaf-count) pairs, 0xFFFF after the
 // trailing interior run of a segment, 0xFFFE after a path.  Returns the number of u16 written (or needed if cap is small).
 uint64_t mmo_trace(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *nodes, uint32_t n_nodes, const uint32_t *indices,
                    const uint8_t *materials, const mm_float4 *emissions, const uint8_t *noise_rgba8, uint32_t noise_w, uint32_t noise_h,

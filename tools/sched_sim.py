@@ -11,6 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mirror_maze_b200 as mm
 from oracle import oracle
 
+octants = []   # per path, per segment: direction octant (filled by get_traces)
 C_I, C_L, C_S, C_O = 103.0, 95.0, 330.0, 10.0     # interior body, leaf body per rect, shade+next-segment, per-iteration vote overhead
 
 
@@ -34,10 +35,16 @@ def get_traces(maze=32, W=1920, H=1080, spp=16, bounces=8, every=97):
     L.mmo_trace(*args, buf.ctypes.data, n)
     # parse into paths: list of segments; segment = list of (run, leafcount) with final (run, None)
     paths, segs, cur = [], [], []
+    octants.clear()
+    octs = []
     it = iter(buf.tolist())
     for tok in it:
         if tok == 0xFFFE:
             paths.append(segs); segs = []
+            octants.append(octs); octs = []
+            continue
+        if (tok & 0xFFF8) == 0xFFF0:
+            octs.append(tok & 7)
             continue
         nxt = next(it)
         if nxt == 0xFFFF:
