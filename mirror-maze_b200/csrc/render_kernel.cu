@@ -203,6 +203,10 @@ __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 or
 // leaf, then all test — left 12 of 32 lanes active in the interior body; see profiles/.)
 // `lit` lanes (operands outside the guarded ranges, or MM_FLAG_FORCE_LITERAL) use the literal-divide slab test.
 constexpr uint32_t kLeafWeight = 3;   // measured best on B200 (profiles/r1_sched_sweep.txt)
+#ifndef MM_INNER_REPS
+#define MM_INNER_REPS 3
+#endif
+constexpr uint32_t kInnerReps = MM_INNER_REPS;
 
 // MIXED = false: no lane of the warp is literal (the common case; the loop then contains no literal-divide code).
 template <bool MIXED, bool SMEM, bool CNT>
@@ -222,13 +226,17 @@ __device__ __forceinline__ void traverse(const PairView<SMEM> &pv, const RectI *
         const unsigned mI = __ballot_sync(0xFFFFFFFFu, isI), mL = __ballot_sync(0xFFFFFFFFu, isL);
         if ((mI | mL) == 0u) break;
         if (mI != 0u && __popc(mI) >= kLeafWeight * __popc(mL)) {
-            if (isI) {
-                float4 bx, by, bz;
-                uint2 lk;
-                pv.load(cur, nx, ny, nz, bx, by, bz, lk);
-                if (CNT) tl.inner++;
-                if (!MIXED || !lit) inner_step<true, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
-                else inner_step<false, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
+            // kInnerReps interior visits per vote: the vote and loop control cost ~18 instructions against ~100 for a visit
+#pragma unroll 1
+            for (uint32_t rep = 0; rep < kInnerReps; rep++) {
+                if ((cur >> 24) == 0u) {
+                    float4 bx, by, bz;
+                    uint2 lk;
+                    pv.load(cur, nx, ny, nz, bx, by, bz, lk);
+                    if (CNT) tl.inner++;
+                    if (!MIXED || !lit) inner_step<true, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
+                    else inner_step<false, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
+                }
             }
         } else {
             if (isL) {

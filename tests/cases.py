@@ -12,6 +12,10 @@ CASES = {
     "cfg2_small": dict(maze=32, W=192, H=108, chunk=4, spp=16, bounce=8, mirror=15),
     # north-star 64x64 maze at small frame
     "maze64": dict(maze=64, W=160, H=88, chunk=4, spp=16, bounce=8, mirror=15),
+    # BASELINE.json configs[2] scaled down: 64x64 maze, 64 spp (T = 1024 threads per virtual group), 16 bounces
+    "cfg3_small": dict(maze=64, W=128, H=72, chunk=4, spp=64, bounce=16, mirror=15),
+    # BASELINE.json configs[3] scaled down: 256x256 maze (BVH depth 21, 43.6 k planes), 8 spp here
+    "maze256": dict(maze=256, W=96, H=64, chunk=4, spp=8, bounce=8, mirror=15),
     # moved and turned camera (mouse yaw, main.rs:923-929), odd time
     "yaw": dict(maze=16, W=128, H=96, chunk=4, spp=8, bounce=8, mirror=15, time=77, center=(25.0, 0.0, -15.0), half_theta=1.1),
     # other chunk widths / spp below 8 (SURVEY §8 D12 generalisation)
