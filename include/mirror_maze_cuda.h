@@ -147,7 +147,7 @@ int mm_upload_scene(mm_ctx *ctx,
  * (main.rs:702-709): created zero-filled at first use (and again when the view size changes), written only
  * at the pixels of the chunks a call renders, kept across calls.  out_rgba is a HOST buffer of
  * view_height*view_width*4 floats, row-major [y][x][rgba], that receives a copy of the whole screen image
- * after the kernel.  counters/debug may be null.
+ * after the kernel; out_rgba may be null when the caller reads the screen later (mm_present).  counters/debug may be null.
  */
 int mm_render(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params,
               const mm_chunk *chunks, uint32_t n_chunks,
@@ -187,6 +187,18 @@ typedef struct mm_scene_info {
     uint32_t smem_bytes, block_threads, blocks_per_sm, n_sms;
 } mm_scene_info;
 int mm_get_scene_info(mm_ctx *ctx, mm_scene_info *out);
+
+/*
+ * f-1 (SURVEY §8 f): the present pass' 5-tap blur, fragment_shader (shaders.metal:214-225, drawn at main.rs:888-892):
+ *   c = img[p];  c += (img[p+(1,0)] + img[p-(1,0)]) / 2;  c += (img[p+(0,1)] + img[p-(0,1)]) / 2;  c /= 3;  img[p] = (c.rgb, 1)
+ * The reference runs it in place on the persistent screen texture every frame (order-dependent read-modify-write
+ * of neighbours); here it is the race-free ping-pong version: every read sees the previous frame's texture, reads
+ * outside the texture return 0.  mm_present blurs the context's persistent screen image (the compute pass'
+ * target) and, when out_rgba is non-null, copies the result to the host buffer (H*W*4 floats).  Synchronous.
+ * mm_present_blur_device is the same kernel on caller device buffers (src != dst), asynchronous.
+ */
+int mm_present(mm_ctx *ctx, float *out_rgba);
+int mm_present_blur_device(mm_ctx *ctx, const float *d_src, float *d_dst, uint32_t width, uint32_t height);
 
 /*
  * Self-test of the kernel's shared-reciprocal slab quotient (see render_kernel.cu header): evaluates n_pairs
@@ -244,6 +256,22 @@ int mm_default_uniform(uint32_t maze_n, float view_width, float view_height, uin
 
 /* f-3 (SURVEY §8 f): player-box collision walk, main.rs:265-291. Returns node index or -1. */
 int mm_check_collision(const mm_bvh_node *nodes, uint32_t n_nodes, mm_float3 bmin, mm_float3 bmax);
+/* f-3: one frame of WASD movement with collision (main.rs:786-826).  keys = macOS key codes in press order
+ * (0 = A, 1 = S, 2 = D, 13 = W; others ignored); each moves by 5/fps along the rotated axis; the move is undone
+ * when the player box center +-(0.5, 0.2, 0.5) overlaps a leaf box.  Returns 1 if the move was blocked, 0 if not. */
+int mm_move_camera(const mm_bvh_node *nodes, uint32_t n_nodes, mm_float3 center, mm_float4 quat, const uint16_t *keys,
+                   uint32_t n_keys, float fps, mm_float3 *out_center);
+
+/* f-1: the progressive-refresh chunk bag, gen_pixels + random_pixels (main.rs:293-326, 713-720, 778-784).  The
+ * reference shuffles with the non-deterministic thread_rng; here the shuffle is rand 0.8.5's Fisher-Yates driven by
+ * StdRng::seed_from_u64(seed).  mm_bag_next pops n chunk origins from the end of the bag and refills it with a clone
+ * of the shuffled original when it runs dry; mm_bag_reshuffle is the regeneration on a rotation change (main.rs:838-839). */
+typedef struct mm_bag mm_bag;
+int mm_bag_new(float view_width, float view_height, uint32_t chunk_width, uint64_t seed, mm_bag **out);
+int mm_bag_free(mm_bag *bag);
+int mm_bag_next(mm_bag *bag, uint32_t n, mm_chunk *out);
+int mm_bag_reshuffle(mm_bag *bag);
+uint32_t mm_bag_size(const mm_bag *bag);
 
 const char *mm_version(void);
 

@@ -111,6 +111,14 @@ PROTOTYPES = {
     "mm_stream": (C.c_int, [_vp, _P(_vp)]),
     "mm_get_scene_info": (C.c_int, [_vp, _P(SceneInfo)]),
     "mm_selftest_quotient": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _P(C.c_uint64)]),
+    "mm_present": (C.c_int, [_vp, _vp]),
+    "mm_present_blur_device": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32]),
+    "mm_move_camera": (C.c_int, [_vp, C.c_uint32, Float3, Float4, _vp, C.c_uint32, C.c_float, _P(Float3)]),
+    "mm_bag_new": (C.c_int, [C.c_float, C.c_float, C.c_uint32, C.c_uint64, _P(_vp)]),
+    "mm_bag_free": (C.c_int, [_vp]),
+    "mm_bag_next": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "mm_bag_reshuffle": (C.c_int, [_vp]),
+    "mm_bag_size": (C.c_uint32, [_vp]),
     "mm_scene_build": (C.c_int, [C.c_uint32, C.c_uint64, C.c_int, _P(_vp)]),
     "mm_scene_free": (C.c_int, [_vp]),
     "mm_scene_n_planes": (C.c_uint32, [_vp]),

@@ -34,6 +34,7 @@ struct mm_ctx {
     Counters *d_counters = nullptr;
     Counters *h_counters = nullptr;   // pinned
     float *d_screen = nullptr;        // persistent screen image (the reference's private screen texture, main.rs:702-709)
+    float *d_screen2 = nullptr;       // ping-pong partner for the present blur
     uint32_t screen_w = 0, screen_h = 0;
     uint32_t *d_dbg_u32[3] = {nullptr, nullptr, nullptr};
     float *d_dbg_rad = nullptr;
@@ -112,7 +113,7 @@ int mm_destroy(mm_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_pairs); cudaFree(ctx->d_rects); cudaFree(ctx->d_shade); cudaFree(ctx->d_noise); cudaFree(ctx->d_chunks);
-    cudaFree(ctx->d_counters); cudaFree(ctx->d_screen); cudaFree(ctx->d_dbg_rad);
+    cudaFree(ctx->d_counters); cudaFree(ctx->d_screen); cudaFree(ctx->d_screen2); cudaFree(ctx->d_dbg_rad);
     for (auto p : ctx->d_dbg_u32) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -276,7 +277,8 @@ int ensure_screen(mm_ctx *ctx, uint32_t W, uint32_t H) {
     if (ctx->d_screen && ctx->screen_w == W && ctx->screen_h == H) return MM_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->d_screen);
-    ctx->d_screen = nullptr;
+    cudaFree(ctx->d_screen2);
+    ctx->d_screen = nullptr; ctx->d_screen2 = nullptr;
     CK(cudaMalloc(&ctx->d_screen, (size_t)W * H * 4 * sizeof(float)));
     CK(cudaMemsetAsync(ctx->d_screen, 0, (size_t)W * H * 4 * sizeof(float), ctx->stream));
     ctx->screen_w = W; ctx->screen_h = H;
@@ -309,7 +311,6 @@ int mm_render(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, const
               float *out_rgba, mm_counters *counters, const mm_debug *debug) {
     if (!ctx) return MM_ERR_INVALID;
     ctx->err.clear();
-    if (!out_rgba) return fail(ctx, MM_ERR_INVALID, "mm_render: null output");
     int rc = mm_set_chunks(ctx, chunks, n_chunks);
     if (rc != MM_OK) return rc;
     const bool dbg = debug && (debug->first_hit || debug->segments || debug->mirror_hits || debug->radiance);
@@ -336,7 +337,7 @@ int mm_render(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, const
     }
     rc = do_launch(ctx, L);
     if (rc != MM_OK) return rc;
-    CK(cudaMemcpyAsync(out_rgba, ctx->d_screen, (size_t)L.p.W * L.p.H * 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_rgba) CK(cudaMemcpyAsync(out_rgba, ctx->d_screen, (size_t)L.p.W * L.p.H * 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (dbg) {
         if (debug->first_hit) CK(cudaMemcpyAsync(debug->first_hit, ctx->d_dbg_u32[0], n_paths * 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (debug->segments) CK(cudaMemcpyAsync(debug->segments, ctx->d_dbg_u32[1], n_paths * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -378,6 +379,29 @@ int mm_set_stream(mm_ctx *ctx, void *stream) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    return MM_OK;
+}
+
+int mm_present_blur_device(mm_ctx *ctx, const float *d_src, float *d_dst, uint32_t width, uint32_t height) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!d_src || !d_dst || d_src == d_dst || width == 0 || height == 0) return fail(ctx, MM_ERR_INVALID, "mm_present_blur_device: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_blur(d_src, d_dst, width, height, ctx->stream));
+    return MM_OK;
+}
+
+int mm_present(mm_ctx *ctx, float *out_rgba) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!ctx->d_screen) return fail(ctx, MM_ERR_INVALID, "mm_present: nothing rendered yet");
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)ctx->screen_w * ctx->screen_h * 4 * sizeof(float);
+    if (!ctx->d_screen2) CK(cudaMalloc(&ctx->d_screen2, bytes));
+    CK(launch_blur(ctx->d_screen, ctx->d_screen2, ctx->screen_w, ctx->screen_h, ctx->stream));
+    float *t = ctx->d_screen; ctx->d_screen = ctx->d_screen2; ctx->d_screen2 = t;   // the blurred image is the screen now
+    if (out_rgba) CK(cudaMemcpyAsync(out_rgba, ctx->d_screen, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return MM_OK;
 }
 

@@ -10,6 +10,21 @@ using namespace mmh;
 
 struct mm_scene { Scene s; };
 struct mm_stdrng { StdRng r; explicit mm_stdrng(uint64_t seed) : r(seed) {} };
+struct mm_bag {
+    float w, h; uint32_t chunk;
+    StdRng rng;
+    std::vector<mm_chunk> original, pixels;
+    mm_bag(float w_, float h_, uint32_t c, uint64_t seed) : w(w_), h(h_), chunk(c), rng(seed) {}
+    void gen() {                                       // gen_pixels (main.rs:293-307)
+        uint32_t n = mm_gen_chunks(w, h, chunk, nullptr, 0);
+        original.resize(n);
+        mm_gen_chunks(w, h, chunk, original.data(), n);
+        for (size_t i = original.size(); i-- > 1;) {   // out_pixels.shuffle(&mut rng)
+            size_t j = rng.gen_range_u32(0, (uint32_t)(i + 1));
+            mm_chunk t = original[i]; original[i] = original[j]; original[j] = t;
+        }
+    }
+};
 
 namespace {
 
@@ -162,6 +177,62 @@ int mm_default_uniform(uint32_t maze_n, float view_width, float view_height, uin
     out->chunk_width = chunk_width;
     out->time = time;
     return MM_OK;
+}
+
+int mm_bag_new(float view_width, float view_height, uint32_t chunk_width, uint64_t seed, mm_bag **out) {
+    if (!out || chunk_width == 0 || !(view_width >= 1.0f) || !(view_height >= 1.0f)) return MM_ERR_INVALID;
+    mm_bag *b = new (std::nothrow) mm_bag(view_width, view_height, chunk_width, seed);
+    if (!b) return MM_ERR_NOMEM;
+    try {
+        b->gen();
+        b->pixels = b->original;                         // main.rs:713-714
+    } catch (...) { delete b; return MM_ERR_NOMEM; }
+    *out = b;
+    return MM_OK;
+}
+int mm_bag_free(mm_bag *bag) { delete bag; return MM_OK; }
+uint32_t mm_bag_size(const mm_bag *bag) { return bag ? (uint32_t)bag->pixels.size() : 0; }
+int mm_bag_next(mm_bag *bag, uint32_t n, mm_chunk *out) {    // random_pixels (main.rs:309-326)
+    if (!bag || !out || bag->original.empty()) return MM_ERR_INVALID;
+    try {
+        for (uint32_t i = 0; i < n; i++) {
+            if (bag->pixels.empty()) bag->pixels = bag->original;   // pixels.append(&mut original.clone())
+            out[i] = bag->pixels.back();
+            bag->pixels.pop_back();
+        }
+    } catch (...) { return MM_ERR_NOMEM; }
+    return MM_OK;
+}
+int mm_bag_reshuffle(mm_bag *bag) {                          // main.rs:838-839
+    if (!bag) return MM_ERR_INVALID;
+    try {
+        bag->gen();
+        bag->pixels = bag->original;
+    } catch (...) { return MM_ERR_NOMEM; }
+    return MM_OK;
+}
+
+int mm_move_camera(const mm_bvh_node *nodes, uint32_t n_nodes, mm_float3 center, mm_float4 quat, const uint16_t *keys,
+                   uint32_t n_keys, float fps, mm_float3 *out_center) {
+    if (!nodes || !out_center || (n_keys && !keys) || !(fps > 0.0f)) return MM_ERR_INVALID;
+    const mm_float3 prev = center;
+    const float step = 5.0f / fps;
+    for (uint32_t i = 0; i < n_keys; i++) {                  // main.rs:787-815
+        mm_float3 dx = {step, 0.0f, 0.0f}, dz = {0.0f, 0.0f, step}, m;
+        switch (keys[i]) {
+            case 0: m = mm_quat_mult(dx, quat); center = {center.x - m.x, center.y - m.y, center.z - m.z}; break;
+            case 1: m = mm_quat_mult(dz, quat); center = {center.x - m.x, center.y - m.y, center.z - m.z}; break;
+            case 2: m = mm_quat_mult(dx, quat); center = {center.x + m.x, center.y + m.y, center.z + m.z}; break;
+            case 13: m = mm_quat_mult(dz, quat); center = {center.x + m.x, center.y + m.y, center.z + m.z}; break;
+            default: break;
+        }
+    }
+    const mm_float3 diag = {0.5f, 0.2f, 0.5f};               // main.rs:738
+    mm_float3 bmin = {center.x - diag.x, center.y - diag.y, center.z - diag.z};
+    mm_float3 bmax = {center.x + diag.x, center.y + diag.y, center.z + diag.z};
+    int blocked = mm_check_collision(nodes, n_nodes, bmin, bmax) >= 0 ? 1 : 0;   // main.rs:817-826
+    *out_center = blocked ? prev : center;
+    return blocked;
 }
 
 int mm_check_collision(const mm_bvh_node *nodes, uint32_t n_nodes, mm_float3 bmin, mm_float3 bmax) {

@@ -526,6 +526,24 @@ __global__ void quot_selftest_kernel(uint64_t n, uint64_t seed, unsigned long lo
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// fragment_shader's 5-tap blur (shaders.metal:214-225), ping-pong: one thread per pixel, one float4 per tap.  HBM-bound:
+// 16 B read + 16 B written per pixel (the four neighbour taps hit L1/L2).
+__global__ void __launch_bounds__(256) blur_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, uint32_t W, uint32_t H) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const size_t row = (size_t)y * W;
+    const float4 c = __ldg(src + row + x);
+    const float4 r = x + 1 < W ? __ldg(src + row + x + 1) : zero, l = x > 0 ? __ldg(src + row + x - 1) : zero;
+    const float4 d = y + 1 < H ? __ldg(src + row + W + x) : zero, u = y > 0 ? __ldg(src + row - W + x) : zero;
+    float4 o;
+    o.x = fdiv(fadd(fadd(c.x, fdiv(fadd(r.x, l.x), 2.0f)), fdiv(fadd(d.x, u.x), 2.0f)), 3.0f);
+    o.y = fdiv(fadd(fadd(c.y, fdiv(fadd(r.y, l.y), 2.0f)), fdiv(fadd(d.y, u.y), 2.0f)), 3.0f);
+    o.z = fdiv(fadd(fadd(c.z, fdiv(fadd(r.z, l.z), 2.0f)), fdiv(fadd(d.z, u.z), 2.0f)), 3.0f);
+    o.w = 1.0f;
+    dst[row + x] = o;
+}
+
 template <bool S, bool C, bool D>
 const void *kptr() { return reinterpret_cast<const void *>(&trace_kernel<S, C, D>); }
 
@@ -544,6 +562,13 @@ cudaError_t launch_trace(const KParams &p, KernelChoice c, unsigned blocks, size
     const void *fn = kernel_ptr(c);
     void *args[] = {const_cast<KParams *>(&p)};
     return cudaLaunchKernel(fn, dim3(blocks), dim3(kBlockThreads), args, smem_bytes, stream);
+}
+
+cudaError_t launch_blur(const float *src, float *dst, uint32_t W, uint32_t H, cudaStream_t stream) {
+    if (W == 0 || H == 0) return cudaSuccess;
+    dim3 grid((W + 255) / 256, H);
+    blur_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), W, H);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_quot_selftest(uint64_t n, uint64_t seed, unsigned long long *d_mismatches, cudaStream_t stream) {

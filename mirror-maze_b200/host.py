@@ -168,3 +168,41 @@ def check_collision(nodes, bmin, bmax):
     nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
     return int(abi.load_library().mm_check_collision(nodes.ctypes.data, len(nodes), Float3(*[float(v) for v in bmin]),
                                                      Float3(*[float(v) for v in bmax])))
+
+
+class ChunkBag:
+    """The progressive-refresh bag of chunk origins: gen_pixels + random_pixels (src/main.rs:293-326, 713-720, 778-784),
+    with a seeded StdRng in place of the reference's non-deterministic thread_rng."""
+
+    def __init__(self, view_width, view_height, chunk_width=4, seed=0):
+        self._lib = abi.load_library()
+        self._h = C.c_void_p()
+        _check(self._lib.mm_bag_new(float(view_width), float(view_height), chunk_width, seed, C.byref(self._h)), "mm_bag_new")
+
+    def next(self, n):
+        out = np.zeros(n, dtype=CHUNK_DTYPE)
+        _check(self._lib.mm_bag_next(self._h, n, out.ctypes.data), "mm_bag_next")
+        return out
+
+    def reshuffle(self):
+        _check(self._lib.mm_bag_reshuffle(self._h), "mm_bag_reshuffle")
+
+    def __len__(self):
+        return int(self._lib.mm_bag_size(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.mm_bag_free(self._h)
+            self._h = None
+
+
+def move_camera(nodes, center, quat, keys, fps=60.0):
+    """One frame of WASD movement with collision (src/main.rs:786-826).  Returns (new_center, blocked)."""
+    nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+    k = np.ascontiguousarray(keys, dtype=np.uint16)
+    out = Float3()
+    rc = abi.load_library().mm_move_camera(nodes.ctypes.data, len(nodes), Float3(*[float(v) for v in center]),
+                                           Float4(*[float(v) for v in quat]), k.ctypes.data, len(k), float(fps), C.byref(out))
+    if rc < 0:
+        raise MMError(rc, "mm_move_camera")
+    return np.array([out.x, out.y, out.z], dtype=np.float32), bool(rc)

@@ -136,6 +136,17 @@ class Renderer:
         self._ck(self._lib.mm_last_counters(self._ctx, C.byref(cnt)))
         return cnt.as_dict()
 
+    def present(self, out=None, copy=True):
+        """The present pass' 5-tap blur over the persistent screen (src/shaders.metal:214-225, src/main.rs:888-892);
+        returns the blurred screen as a host array when copy is true."""
+        if copy and out is None:
+            raise ValueError("pass the host array that receives the frame")
+        self._ck(self._lib.mm_present(self._ctx, out.ctypes.data if copy else None))
+        return out
+
+    def present_blur_device(self, src_ptr, dst_ptr, width, height):
+        self._ck(self._lib.mm_present_blur_device(self._ctx, src_ptr, dst_ptr, width, height))
+
     def selftest_quotient(self, n_pairs, seed=1):
         """Mismatches between the shared-reciprocal slab quotient and __fdiv_rn over n_pairs samples (must be 0)."""
         bad = C.c_uint64()

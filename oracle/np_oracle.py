@@ -316,3 +316,20 @@ def _render(sc, noise, U_, P, chunks):
     image[fy[ok], fx[ok], 3] = F(1.0)
     debug = {"first_hit": first_hit, "segments": segments, "mirror_hits": mirror_hits.astype(U), "radiance": radiance}
     return image, counters, debug
+
+
+def present_blur(img):
+    """fragment_shader (reference src/shaders.metal:214-225) as a race-free ping-pong pass over an [H,W,4] float32 image:
+    c = img[p]; c += (img[p+(1,0)] + img[p-(1,0)]) / 2; c += (img[p+(0,1)] + img[p-(0,1)]) / 2; c /= 3; out = (c.rgb, 1).
+    Reads outside the texture return 0."""
+    img = np.asarray(img, dtype=F)
+    H, W = img.shape[:2]
+    pad = np.zeros((H + 2, W + 2, 4), dtype=F)
+    pad[1:-1, 1:-1] = img
+    c = pad[1:-1, 1:-1]
+    r, l = pad[1:-1, 2:], pad[1:-1, :-2]
+    d, u = pad[2:, 1:-1], pad[:-2, 1:-1]
+    o = (c + (r + l) / F(2.0)) + (d + u) / F(2.0)
+    o = o / F(3.0)
+    o[..., 3] = F(1.0)
+    return o.astype(F)

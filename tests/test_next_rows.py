@@ -1,0 +1,106 @@
+"""f-1 progressive chunk bag + present blur (reference src/main.rs:293-326,778-784;
+src/shaders.metal:214-225), f-3 scripted camera movement with collision (src/main.rs:786-826, 265-291)."""
+import numpy as np
+import pytest
+
+from cases import build_case
+
+F = np.float32
+
+
+def test_chunk_bag_matches_random_pixels_semantics(mm):
+    from oracle import host_ref
+
+    W, H, chunk, seed = 64, 48, 4, 5
+    bag = mm.ChunkBag(W, H, chunk, seed)
+    # Python restatement: gen_pixels order, Fisher-Yates from the top with StdRng, pop from the end, refill with a clone
+    rng = host_ref.StdRng(seed)
+    original = [(chunk * i, chunk * j) for i in range(W // chunk) for j in range(H // chunk)]
+    for i in range(len(original) - 1, 0, -1):
+        j = rng.gen_range(0, i + 1)
+        original[i], original[j] = original[j], original[i]
+    pixels = list(original)
+    for take in (7, 100, 85, 192, 3):                                     # crosses the refill boundary (192 chunks)
+        want = []
+        for _ in range(take):
+            if not pixels:
+                pixels = list(original)
+            want.append(pixels.pop())
+        got = bag.next(take)
+        assert [(int(c["x"]), int(c["y"])) for c in got] == want
+    assert len(bag) == len(pixels)
+    seen = mm.ChunkBag(W, H, chunk, seed).next(192)
+    assert sorted((int(c["x"]), int(c["y"])) for c in seen) == sorted(original)   # one full bag covers the screen once
+
+
+def test_move_camera_and_collision(mm, scenes):
+    sc = scenes(10)
+    u = mm.default_uniform(10, 64, 64)
+    q = [u.cam.rotation.x, u.cam.rotation.y, u.cam.rotation.z, u.cam.rotation.w]
+    c0 = np.array([u.cam.camera_center.x, u.cam.camera_center.y, u.cam.camera_center.z], dtype=F)
+    c1, blocked = mm.move_camera(sc.nodes, c0, q, [13], fps=60.0)          # W: forward along the rotated +z
+    assert not blocked
+    step = mm.quat_mult([0.0, 0.0, F(5.0) / F(60.0)], q)
+    assert c1.tobytes() == (c0 + step).astype(F).tobytes()
+    c2, _ = mm.move_camera(sc.nodes, c1, q, [1], fps=60.0)                 # S undoes it (up to rounding)
+    assert np.allclose(c2, c0, atol=1e-6)
+    c3, _ = mm.move_camera(sc.nodes, c0, q, [99], fps=60.0)                # unknown key: no move
+    assert c3.tobytes() == c0.tobytes()
+    near_wall = np.array([-5.0, 0.0, -49.6], dtype=F)                     # 0.4 from the z = -50 outer wall, facing it
+    c4, blocked = mm.move_camera(sc.nodes, near_wall, q, [1], fps=60.0)    # S moves backwards into the wall
+    assert blocked and c4.tobytes() == near_wall.tobytes()
+
+
+def test_blur_reference_model():
+    from oracle import np_oracle
+
+    img = np.zeros((3, 4, 4), dtype=F)
+    img[1, 1] = [3.0, 6.0, 9.0, 1.0]
+    out = np_oracle.present_blur(img)
+    assert out[1, 1, :3].tolist() == [1.0, 2.0, 3.0]                      # centre / 3
+    assert out[1, 2, :3].tolist() == [0.5, 1.0, 1.5] and out[0, 1, :3].tolist() == [0.5, 1.0, 1.5]   # neighbour / 2 / 3
+    assert out[0, 0, :3].tolist() == [0.0, 0.0, 0.0] and (out[..., 3] == 1).all()
+
+
+@pytest.mark.gpu
+def test_present_blur_matches_model(mm, renderer):
+    import torch
+    from oracle import np_oracle
+
+    rng = np.random.default_rng(3)
+    for (H, W) in ((1, 1), (5, 7), (33, 257), (270, 480)):
+        img = rng.random((H, W, 4), dtype=np.float32)
+        src = torch.from_numpy(img).cuda()
+        dst = torch.empty_like(src)
+        torch.cuda.synchronize()
+        renderer.present_blur_device(src.data_ptr(), dst.data_ptr(), W, H)
+        renderer.sync()
+        assert dst.cpu().numpy().tobytes() == np_oracle.present_blur(img).tobytes()
+
+
+@pytest.mark.gpu
+def test_progressive_refresh_frame_loop(mm, oracle, noise, scenes):
+    """Three frames of the reference's loop (main.rs:778-784, 867-893): pop a bag of chunks, render them into the
+    persistent screen, blur the whole screen — GPU against the oracle + numpy composition, bit for bit."""
+    from oracle import np_oracle
+
+    sc, u, p, _ = build_case(mm, "yaw", scenes)
+    W, H = int(u.view_width), int(u.view_height)
+    r = mm.Renderer(0)
+    r.upload_scene(sc, noise)
+    bag_gpu, bag_cpu = mm.ChunkBag(W, H, 4, seed=9), mm.ChunkBag(W, H, 4, seed=9)
+    q = mm.Params.from_buffer_copy(bytes(p))
+    q.grid_x, q.grid_y = 16, 6                                             # 96 of 768 chunks per frame
+    screen = np.zeros((H, W, 4), dtype=F)
+    out = np.zeros((H, W, 4), dtype=F)
+    for frame in range(3):
+        u.time = frame
+        chunks = bag_gpu.next(96)
+        r.render(u, q, chunks)
+        r.present(out)
+        ref_chunks = bag_cpu.next(96)
+        assert chunks.tobytes() == ref_chunks.tobytes()
+        oracle.render(sc, noise, u, q, ref_chunks, out=screen)             # writes only the rendered chunks
+        screen = np_oracle.present_blur(screen)
+        assert out.tobytes() == screen.tobytes(), f"frame {frame}"
+    r.close()
