@@ -88,3 +88,14 @@ def test_product_never_imports_oracle():
                 for needle in ("libmm_oracle", "from oracle", "import oracle", "np_oracle", "mmo_render", "oracle/_ref", "dlopen"):
                     assert needle not in text, f"{f} references the oracle ({needle})"
                 assert not re.search(r'#include\s*["<][^">]*oracle', text), f"{f} includes oracle code"
+
+
+def test_headless_driver_fails_loudly_without_gpu(mm):
+    import subprocess
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    exe = os.path.join(os.path.dirname(mm.library_path()), "mm_headless")
+    out = subprocess.run([exe, "--maze", "4", "--width", "16", "--height", "16", "--spp", "1"], capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0 and "mm_create failed" in out.stderr

@@ -247,3 +247,23 @@ def test_single_leaf_and_tiny_scenes(mm, oracle, noise, renderer):
         p = mm.full_frame_params(u, spp=8, bounce_limit=3)
         renderer.upload_scene(s, noise)
         assert_same(renderer.render(u, p, ch, debug=True), oracle.render(s, noise, u, p, ch, debug=True))
+
+
+def test_headless_cpp_driver_matches_python_binding(mm, noise, scenes, tmp_path):
+    """mm_headless (C++ consumer of the C-ABI, the stand-in for the Rust driver) renders the same bits as the ctypes path."""
+    import os
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(mm.library_path()), "mm_headless")
+    raw, nz = tmp_path / "frame.f32", tmp_path / "noise.rgba8"
+    nz.write_bytes(noise.tobytes())
+    out = subprocess.run([exe, "--maze", "16", "--width", "128", "--height", "96", "--spp", "8", "--bounces", "6", "--noise", str(nz),
+                          "--raw", str(raw)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    sc = scenes(16)
+    r = mm.Renderer(0)
+    r.upload_scene(sc, noise)
+    u = mm.default_uniform(16, 128, 96, 4)
+    img = r.render(u, mm.full_frame_params(u, spp=8, bounce_limit=6), mm.gen_chunks(128, 96, 4))[0]
+    assert raw.read_bytes() == img.tobytes()
+    r.close()
