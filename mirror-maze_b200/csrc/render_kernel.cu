@@ -106,15 +106,35 @@ struct PairView {
     const uint2 *l;
     const PairRec *g;
     uint32_t n_pairs;
+};
+
+// Per-ray view: the three per-axis base pointers already include the travel-order choice, so that a visit's address
+// arithmetic is one multiply-add per load.
+template <bool SMEM>
+struct RayPairs {
+    const char *bx, *by, *bz, *bl;
     // nx/ny/nz: 1 when the ray travels down that axis (fast path only; the literal path always passes 0)
-    __device__ __forceinline__ void load(uint32_t p, uint32_t nx, uint32_t ny, uint32_t nz, float4 &bx, float4 &by, float4 &bz,
-                                         uint2 &lk) const {
+    __device__ __forceinline__ RayPairs(const PairView<SMEM> &pv, uint32_t nx, uint32_t ny, uint32_t nz) {
         if (SMEM) {
-            bx = x[p + nx * n_pairs]; by = y[p + ny * n_pairs]; bz = z[p + nz * n_pairs]; lk = l[p];
+            bx = reinterpret_cast<const char *>(pv.x + nx * pv.n_pairs);
+            by = reinterpret_cast<const char *>(pv.y + ny * pv.n_pairs);
+            bz = reinterpret_cast<const char *>(pv.z + nz * pv.n_pairs);
+            bl = reinterpret_cast<const char *>(pv.l);
         } else {
-            const float4 *pp = reinterpret_cast<const float4 *>(g + p);
-            bx = __ldg(pp + 4 * nx); by = __ldg(pp + 1 + 4 * ny); bz = __ldg(pp + 2 + 4 * nz);
-            lk = __ldg(reinterpret_cast<const uint2 *>(pp + 3));
+            const char *b = reinterpret_cast<const char *>(pv.g);
+            bx = b + 64 * nx; by = b + 16 + 64 * ny; bz = b + 32 + 64 * nz; bl = b + 48;
+            // keep the three pointers live: ptxas otherwise re-derives them from sign(dir) at every node (5 instructions each)
+            asm("" : "+l"(bx)); asm("" : "+l"(by)); asm("" : "+l"(bz));
+        }
+    }
+    __device__ __forceinline__ void load(uint32_t p, float4 &vx, float4 &vy, float4 &vz, uint2 &lk) const {
+        if (SMEM) {
+            vx = *reinterpret_cast<const float4 *>(bx + 16u * p); vy = *reinterpret_cast<const float4 *>(by + 16u * p);
+            vz = *reinterpret_cast<const float4 *>(bz + 16u * p); lk = *reinterpret_cast<const uint2 *>(bl + 8u * p);
+        } else {
+            const size_t off = (size_t)p * sizeof(PairRec);
+            vx = __ldg(reinterpret_cast<const float4 *>(bx + off)); vy = __ldg(reinterpret_cast<const float4 *>(by + off));
+            vz = __ldg(reinterpret_cast<const float4 *>(bz + off)); lk = __ldg(reinterpret_cast<const uint2 *>(bl + off));
         }
     }
 };
@@ -209,15 +229,27 @@ constexpr uint32_t kLeafWeight = 3;   // measured best on B200 (profiles/r1_sche
 constexpr uint32_t kInnerReps = MM_INNER_REPS;
 
 // MIXED = false: no lane of the warp is literal (the common case; the loop then contains no literal-divide code).
+// Not inlined on purpose: the call boundary parks the path state that the traversal does not touch (throughput,
+// radiance, RNG state, counters, pixel bookkeeping) in the caller's frame, so the traversal loop has the whole 64-register
+// budget and keeps its per-ray constants (reciprocal corrections, travel-order offsets, table base) live instead of
+// rematerialising them at every node.
+struct Hit { float t; uint32_t slot; };
+#ifndef MM_TRAVERSE_INLINE
+#define MM_TRAVERSE_ATTR __noinline__
+#else
+#define MM_TRAVERSE_ATTR __forceinline__
+#endif
 template <bool MIXED, bool SMEM, bool CNT>
-__device__ __forceinline__ void traverse(const PairView<SMEM> &pv, const RectI *__restrict__ rects, uint32_t root, bool alive, bool lit,
-                                         V3 ori, V3 dir, float &beam_t, uint32_t &beam_slot, uint32_t *stack, Tally &tl) {
+__device__ MM_TRAVERSE_ATTR Hit traverse(PairView<SMEM> pv, const RectI *__restrict__ rects, uint32_t root, bool alive, bool lit,
+                                         V3 ori, V3 dir, float beam_t, uint32_t beam_slot, uint32_t *stack, Tally *tlp) {
+    Tally tl = {0u, 0u, 0u, 0u};
     Axis ax, ay, az;
     ax.o = ori.x; ax.d = dir.x; ay.o = ori.y; ay.d = dir.y; az.o = ori.z; az.d = dir.z;
     ax.r = __frcp_rn(ax.d); ax.rl = fmul(__fmaf_rn(-ax.d, ax.r, 1.0f), ax.r);
     ay.r = __frcp_rn(ay.d); ay.rl = fmul(__fmaf_rn(-ay.d, ay.r, 1.0f), ay.r);
     az.r = __frcp_rn(az.d); az.rl = fmul(__fmaf_rn(-az.d, az.r, 1.0f), az.r);
     const uint32_t nx = (!lit && ax.d < 0.0f) ? 1u : 0u, ny = (!lit && ay.d < 0.0f) ? 1u : 0u, nz = (!lit && az.d < 0.0f) ? 1u : 0u;
+    const RayPairs<SMEM> rp(pv, nx, ny, nz);
     uint32_t cur = alive ? root : CUR_END, head = 0, slot = beam_slot;
     float t = beam_t;
     while (true) {
@@ -232,7 +264,7 @@ __device__ __forceinline__ void traverse(const PairView<SMEM> &pv, const RectI *
                 if ((cur >> 24) == 0u) {
                     float4 bx, by, bz;
                     uint2 lk;
-                    pv.load(cur, nx, ny, nz, bx, by, bz, lk);
+                    rp.load(cur, bx, by, bz, lk);
                     if (CNT) tl.inner++;
                     if (!MIXED || !lit) inner_step<true, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
                     else inner_step<false, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
@@ -245,8 +277,10 @@ __device__ __forceinline__ void traverse(const PairView<SMEM> &pv, const RectI *
             }
         }
     }
-    beam_t = t;
-    beam_slot = slot;
+    if (CNT) { tlp->inner += tl.inner; tlp->leaf += tl.leaf; tlp->rect += tl.rect; tlp->max_stack = max(tlp->max_stack, tl.max_stack); }
+    Hit h;
+    h.t = t; h.slot = slot;
+    return h;
 }
 
 // noise.sample(s, float2(gid)): normalised coordinates, address::repeat, filter::nearest (shaders.metal:288,291).
@@ -355,8 +389,10 @@ trace_kernel(const __grid_constant__ KParams P) {
         while (__any_sync(0xFFFFFFFFu, alive)) {
             const bool lit = P.force_literal || !P.scene_fast_ok ||
                              !(axis_safe(ori.x, dir.x) && axis_safe(ori.y, dir.y) && axis_safe(ori.z, dir.z));
-            if (!__any_sync(0xFFFFFFFFu, alive && lit)) traverse<false, SMEM_NODES, CNT>(pv, P.rects, root, alive, false, ori, dir, t, slot, stack, tl);
-            else traverse<true, SMEM_NODES, CNT>(pv, P.rects, root, alive, lit, ori, dir, t, slot, stack, tl);
+            Hit h;
+            if (!__any_sync(0xFFFFFFFFu, alive && lit)) h = traverse<false, SMEM_NODES, CNT>(pv, P.rects, root, alive, false, ori, dir, t, slot, stack, &tl);
+            else h = traverse<true, SMEM_NODES, CNT>(pv, P.rects, root, alive, lit, ori, dir, t, slot, stack, &tl);
+            t = h.t; slot = h.slot;
             if (alive) {
                 if (lit) nliteral++;
                 seg++;

@@ -75,10 +75,10 @@ struct KParams {
 };
 
 #ifndef MM_BLOCK_THREADS
-#define MM_BLOCK_THREADS 512
+#define MM_BLOCK_THREADS 256
 #endif
 #ifndef MM_MIN_BLOCKS
-#define MM_MIN_BLOCKS 2
+#define MM_MIN_BLOCKS 4
 #endif
 constexpr int kBlockThreads = MM_BLOCK_THREADS;   // 32 warps/SM at <= 64 registers (measured best; profiles/r1_block_shape.txt)
 
