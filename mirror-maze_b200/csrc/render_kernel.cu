@@ -248,6 +248,9 @@ __device__ MM_TRAVERSE_ATTR Hit traverse(PairView<SMEM> pv, const RectI *__restr
     ax.r = __frcp_rn(ax.d); ax.rl = fmul(__fmaf_rn(-ax.d, ax.r, 1.0f), ax.r);
     ay.r = __frcp_rn(ay.d); ay.rl = fmul(__fmaf_rn(-ay.d, ay.r, 1.0f), ay.r);
     az.r = __frcp_rn(az.d); az.rl = fmul(__fmaf_rn(-az.d, az.r, 1.0f), az.r);
+#ifdef MM_PIN_RL
+    asm("" : "+f"(ax.rl)); asm("" : "+f"(ay.rl)); asm("" : "+f"(az.rl));   // keep the reciprocal corrections live (no per-node rematerialisation)
+#endif
     const uint32_t nx = (!lit && ax.d < 0.0f) ? 1u : 0u, ny = (!lit && ay.d < 0.0f) ? 1u : 0u, nz = (!lit && az.d < 0.0f) ? 1u : 0u;
     const RayPairs<SMEM> rp(pv, nx, ny, nz);
     uint32_t cur = alive ? root : CUR_END, head = 0, slot = beam_slot;

@@ -29,12 +29,17 @@ CASES = {
     "bounce1": dict(maze=10, W=32, H=32, chunk=4, spp=8, bounce=1, mirror=15),
     # camera outside the box looking away: every path misses on the first segment
     "all_miss": dict(maze=10, W=32, H=32, chunk=4, spp=8, bounce=4, mirror=15, center=(0.0, 0.0, -500.0), half_theta=3.14159),
+    # camera x within 2^-40 of 0 but not 0: outside the guarded range of the shared-reciprocal slab test, so every
+    # primary ray takes the literal-divide traversal while later segments take the fast one (mixed warps)
+    "tiny_origin": dict(maze=10, W=64, H=32, chunk=4, spp=8, bounce=4, mirror=15, center=(1e-20, 0.0, -45.0)),
+    # camera exactly on a wall plane coordinate (x = 0): quotients that are exactly 0 and 0/0-free ties
+    "on_plane": dict(maze=16, W=64, H=32, chunk=4, spp=8, bounce=5, mirror=15, center=(0.0, 0.0, -75.0), half_theta=0.3),
     # ragged: frame not a multiple of the chunk => gen_chunks floors (main.rs:294-295) and border pixels stay unwritten
     "ragged": dict(maze=10, W=50, H=30, chunk=4, spp=8, bounce=3, mirror=15),
 }
 
 # cases small enough for the numpy transcription
-NP_CASES = ["cfg1", "yaw", "chunk2_spp4", "chunk8_spp2", "chunk3_spp32", "mirror_limit2", "bounce0", "bounce1", "all_miss", "ragged"]
+NP_CASES = ["cfg1", "yaw", "tiny_origin", "on_plane", "chunk2_spp4", "chunk8_spp2", "chunk3_spp32", "mirror_limit2", "bounce0", "bounce1", "all_miss", "ragged"]
 
 
 def build_case(mm, name, scenes=None):

@@ -267,3 +267,32 @@ def test_headless_cpp_driver_matches_python_binding(mm, noise, scenes, tmp_path)
     img = r.render(u, mm.full_frame_params(u, spp=8, bounce_limit=6), mm.gen_chunks(128, 96, 4))[0]
     assert raw.read_bytes() == img.tobytes()
     r.close()
+
+
+def test_random_poses_match_oracle(mm, oracle, noise, scenes, renderer):
+    """24 seeded camera poses (cell centres, arbitrary yaw, odd `time`) in the 32x32 maze: every observable bit-identical."""
+    sc = scenes(32)
+    renderer.upload_scene(sc, noise)
+    rng = np.random.default_rng(1)
+    ch = mm.gen_chunks(48, 32, 4)
+    literal_total = 0
+    for i in range(24):
+        cell = rng.integers(0, 32, size=2)
+        center = (-160.0 + 10.0 * cell[0] + 5.0, float(rng.uniform(-6.0, 1.5)), -160.0 + 10.0 * cell[1] + 5.0)
+        u = mm.default_uniform(32, 48, 32, 4, time=int(rng.integers(0, 1000)), camera_center=center,
+                               half_theta=float(rng.uniform(0.0, np.pi)))
+        p = mm.full_frame_params(u, spp=4, bounce_limit=8)
+        got = renderer.render(u, p, ch, debug=True)
+        assert_same(got, oracle.render(sc, noise, u, p, ch, debug=True))
+        literal_total += got[1]["literal_rays"]
+    assert literal_total >= 0
+
+
+def test_literal_lanes_inside_fast_warps(mm, oracle, noise, scenes, renderer):
+    """tiny_origin: the camera's |x| < 2^-40 pushes every primary ray onto the literal-divide traversal."""
+    sc, u, p, ch = build_case(mm, "tiny_origin", scenes)
+    renderer.upload_scene(sc, noise)
+    img, cnt, dbg = renderer.render(u, p, ch, debug=True)
+    assert cnt["literal_rays"] >= cnt["paths"]            # at least the primary segment of every path
+    assert cnt["literal_rays"] < cnt["rays"]              # later segments are back on the fast path
+    assert_same((img, cnt, dbg), oracle.render(sc, noise, u, p, ch, debug=True))
