@@ -230,13 +230,6 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
     p.noise_w = ctx->noise_w; p.noise_h = ctx->noise_h;
     p.force_literal = (par->flags & MM_FLAG_FORCE_LITERAL) ? 1u : 0u;
     p.scene_fast_ok = ctx->fast_ok ? 1u : 0u;
-    p.th_inner = 16; p.w_inner = 1; p.w_leaf = 3; p.w_shade = 1;   // measured best on B200 (profiles/r1_sched_sweep.txt)
-    if (const char *e = getenv("MM_SCHED")) {   // tuning hook: "th,wI,wL,wS"
-        unsigned a, b, c, d;
-        if (sscanf(e, "%u,%u,%u,%u", &a, &b, &c, &d) == 4 && a >= 1 && b >= 1 && c >= 1 && d >= 1) {   // th = 0 would never leave the loop
-            p.th_inner = a; p.w_inner = b; p.w_leaf = c; p.w_shade = d;
-        }
-    }
     p.total_paths = (uint64_t)count * T;
     p.pairs = ctx->d_pairs; p.rects = ctx->d_rects; p.shade = ctx->d_shade;
     p.chunks = ctx->d_chunks; p.noise = ctx->d_noise;

@@ -58,8 +58,6 @@ struct KParams {
     uint32_t root_link, root_count;   // descriptor of node 0 (pair 0 unless the root is a leaf)
     uint32_t noise_w, noise_h;
     uint32_t force_literal;
-    uint32_t th_inner, w_inner, w_leaf, w_shade;   // warp scheduler: run the interior body when >= th_inner lanes want it, else the
-                                                   // body with the largest weighted lane count
     uint32_t scene_fast_ok;
     uint64_t total_paths;
     const PairRec *pairs;

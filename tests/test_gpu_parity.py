@@ -296,3 +296,20 @@ def test_literal_lanes_inside_fast_warps(mm, oracle, noise, scenes, renderer):
     assert cnt["literal_rays"] >= cnt["paths"]            # at least the primary segment of every path
     assert cnt["literal_rays"] < cnt["rays"]              # later segments are back on the fast path
     assert_same((img, cnt, dbg), oracle.render(sc, noise, u, p, ch, debug=True))
+
+
+def test_full_size_frame_equals_oracle(mm, noise, scenes, renderer):
+    """BASELINE configs[1] at FULL size — 32x32 maze, 1920x1080, 16 spp, 8 bounces, 33.2 M paths, 268 M rays — the whole
+    frame and every counter against the CPU oracle (about 10-20 s of host time on the GPU box's cores)."""
+    from oracle import oracle as o
+
+    sc = scenes(32)
+    renderer.upload_scene(sc, noise)
+    u = mm.default_uniform(32, 1920, 1080, 4)
+    ch = mm.gen_chunks(1920, 1080, 4)
+    p = mm.full_frame_params(u, spp=16, bounce_limit=8, flags=mm.FLAG_COUNTERS)
+    img, cnt, _ = renderer.render(u, p, ch)
+    ref, rcnt, _ = o.render(sc, noise, u, p, ch)
+    assert img.tobytes() == ref.tobytes()
+    for k in COUNTER_KEYS:
+        assert cnt[k] == rcnt[k], k
