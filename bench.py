@@ -279,7 +279,7 @@ def run_ours(a):
         e2e_s, e2e_rays = float(tmax[0].item()), int(t[1].item())
         h2d = len(chunks) * 8 + ctypes.sizeof(mm.Uniform) + ctypes.sizeof(mm.Params)
         d2h = H * W * 16
-        e2e_launches = 1 + world
+        e2e_launches = 2
 
     if rank != 0:
         if dist is not None:
@@ -333,8 +333,8 @@ def run_ours(a):
             "e2e": {"value": round(e2e_rays / e2e_s / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": round(1e3 * e2e_s / e2e_steps, 4), "steps": e2e_steps,
                     "api": "mm_render (host chunk list + uniform in, host frame out)" if world == 1 else
-                           "mm_set_chunks + mm_render_device + NCCL all-gather + mm_scatter_tiles_device + frame to pinned host on rank 0"},
-            "gpu_launches": a.steps * (1 if world == 1 else 1 + world), "counters": cnt_frame}
+                           "mm_set_chunks + mm_render_device + NCCL all-gather + mm_scatter_gathered_device + frame to pinned host on rank 0"},
+            "gpu_launches": a.steps * (1 if world == 1 else 2), "counters": cnt_frame}
     if not a.no_cpu_baseline and world == 1:
         val, cinfo = cpu_reference_run(a, 1, 0)
         line["cpu_baseline"] = {"value": round(val, 3), "unit": UNIT, "cores": cinfo["cores"], "kind": "port", "sample": cinfo["sample"]}

@@ -169,6 +169,10 @@ int mm_render_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params
  * group_first + k*group_step.  Asynchronous on the context's stream. */
 int mm_scatter_tiles_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params,
                             const float *d_tiles, float *d_image);
+/* The same for a whole all-gather result in one launch: d_gathered = world x max_count tiles, rank r's tile k at
+ * row r*max_count + k, holding group r + k*world (the interleaved partition of tile_partition / TiledFrameRenderer). */
+int mm_scatter_gathered_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, uint32_t world, uint32_t max_count,
+                               const float *d_gathered, float *d_image);
 int mm_sync(mm_ctx *ctx);
 /* Run the context's work on a caller-owned cudaStream_t (e.g. torch's current stream) from now on; NULL
  * restores the context's own stream.  The caller keeps the stream alive while the context uses it. */

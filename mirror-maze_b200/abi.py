@@ -104,6 +104,7 @@ PROTOTYPES = {
     "mm_set_chunks": (C.c_int, [_vp, _vp, C.c_uint32]),
     "mm_render_device": (C.c_int, [_vp, _P(Uniform), _P(Params), _vp, _vp]),
     "mm_scatter_tiles_device": (C.c_int, [_vp, _P(Uniform), _P(Params), _vp, _vp]),
+    "mm_scatter_gathered_device": (C.c_int, [_vp, _P(Uniform), _P(Params), C.c_uint32, C.c_uint32, _vp, _vp]),
     "mm_sync": (C.c_int, [_vp]),
     "mm_set_stream": (C.c_int, [_vp, _vp]),
     "mm_last_counters": (C.c_int, [_vp, _P(Counters)]),

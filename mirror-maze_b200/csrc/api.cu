@@ -41,6 +41,8 @@ struct mm_ctx {
     size_t dbg_cap = 0;
     // last launch facts
     uint32_t last_smem = 0, last_blocks_per_sm = 0;
+    const void *cfg_fn = nullptr;     // kernel variant whose attributes / occupancy were last set up
+    size_t cfg_smem = 0;
     bool last_smem_nodes = false;
 };
 
@@ -251,10 +253,13 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
 
 int do_launch(mm_ctx *ctx, Launch &L) {
     const void *fn = kernel_ptr(L.choice);
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlockThreads, L.smem));
-    ctx->last_blocks_per_sm = (uint32_t)per_sm;
+    if (fn != ctx->cfg_fn || L.smem != ctx->cfg_smem) {   // once per kernel variant, not per frame
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlockThreads, L.smem));
+        ctx->last_blocks_per_sm = (uint32_t)per_sm;
+        ctx->cfg_fn = fn; ctx->cfg_smem = L.smem;
+    }
     ctx->last_smem = (uint32_t)L.smem;
     ctx->last_smem_nodes = L.choice.smem_nodes;
     CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->stream));
@@ -355,6 +360,22 @@ int mm_scatter_tiles_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params 
     CK(cudaSetDevice(ctx->device));
     CK(launch_scatter(d_tiles, d_image, ctx->d_chunks, (uint32_t)n_groups, first, step, count, uni->chunk_width, (uint32_t)uni->view_width,
                       (uint32_t)uni->view_height, ctx->stream));
+    return MM_OK;
+}
+
+int mm_scatter_gathered_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, uint32_t world, uint32_t max_count,
+                               const float *d_gathered, float *d_image) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!uni || !params || !d_gathered || !d_image || world == 0 || max_count == 0)
+        return fail(ctx, MM_ERR_INVALID, "mm_scatter_gathered_device: bad argument");
+    if (!ctx->d_chunks) return fail(ctx, MM_ERR_INVALID, "mm_scatter_gathered_device: no chunk list set");
+    const uint64_t n_groups = (uint64_t)params->grid_x * params->grid_y;
+    if (n_groups != ctx->n_chunks) return fail(ctx, MM_ERR_INVALID, "grid_x*grid_y must equal the chunk count");
+    if ((uint64_t)world * max_count < n_groups) return fail(ctx, MM_ERR_INVALID, "gathered buffer smaller than the grid");
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_scatter_all(d_gathered, d_image, ctx->d_chunks, world, max_count, (uint32_t)n_groups, uni->chunk_width,
+                          (uint32_t)uni->view_width, (uint32_t)uni->view_height, ctx->stream));
     return MM_OK;
 }
 

@@ -522,6 +522,21 @@ __global__ void scatter_kernel(const float4 *__restrict__ tiles, float4 *__restr
     if (x < W && y < H) image[(size_t)y * W + x] = tiles[i];
 }
 
+// The whole all-gather result in one launch: rank r's tile k is group r + k*world (the interleaved partition).
+__global__ void scatter_all_kernel(const float4 *__restrict__ gathered, float4 *__restrict__ image, const mm_chunk *__restrict__ chunks,
+                                   uint32_t world, uint32_t max_count, uint32_t n_groups, uint32_t chunk, uint32_t ppc, uint32_t W, uint32_t H) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)world * max_count * ppc) return;
+    const uint32_t pn = (uint32_t)(i % ppc);
+    const uint64_t tile = i / ppc;
+    const uint32_t r = (uint32_t)(tile / max_count), k = (uint32_t)(tile % max_count);
+    const uint64_t g = (uint64_t)r + (uint64_t)k * world;
+    if (g >= n_groups) return;                         // padding rows of ranks that own one group less
+    const mm_chunk ch = chunks[g];
+    const uint32_t x = ch.x + pn / chunk, y = ch.y + pn % chunk;
+    if (x < W && y < H) image[(size_t)y * W + x] = gathered[i];
+}
+
 // Self-test of the shared-reciprocal quotient against __fdiv_rn on pseudo-random operands inside the guarded ranges
 // (|d| in [2^-60, 2^60], x = 0 or |x| in [2^-40, 2^31]); half of the samples are built to land within a few
 // 2^-24 ulp of a rounding midpoint, the only place where a faithful-but-not-exact quotient could differ.
@@ -601,6 +616,17 @@ cudaError_t launch_trace(const KParams &p, KernelChoice c, unsigned blocks, size
     const void *fn = kernel_ptr(c);
     void *args[] = {const_cast<KParams *>(&p)};
     return cudaLaunchKernel(fn, dim3(blocks), dim3(kBlockThreads), args, smem_bytes, stream);
+}
+
+cudaError_t launch_scatter_all(const float *gathered, float *image, const mm_chunk *chunks, uint32_t world, uint32_t max_count,
+                               uint32_t n_groups, uint32_t chunk, uint32_t W, uint32_t H, cudaStream_t stream) {
+    const uint32_t ppc = chunk * chunk;
+    const uint64_t n = (uint64_t)world * max_count * ppc;
+    if (n == 0) return cudaSuccess;
+    scatter_all_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4 *>(gathered),
+                                                                       reinterpret_cast<float4 *>(image), chunks, world, max_count,
+                                                                       n_groups, chunk, ppc, W, H);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_blur(const float *src, float *dst, uint32_t W, uint32_t H, cudaStream_t stream) {

@@ -128,6 +128,9 @@ class Renderer:
     def scatter_tiles_device(self, uniform, params, tiles_ptr, image_ptr):
         self._ck(self._lib.mm_scatter_tiles_device(self._ctx, C.byref(uniform), C.byref(params), tiles_ptr, image_ptr))
 
+    def scatter_gathered_device(self, uniform, params, world, max_count, gathered_ptr, image_ptr):
+        self._ck(self._lib.mm_scatter_gathered_device(self._ctx, C.byref(uniform), C.byref(params), world, max_count, gathered_ptr, image_ptr))
+
     def sync(self):
         self._ck(self._lib.mm_sync(self._ctx))
 
@@ -202,10 +205,5 @@ class TiledFrameRenderer:
             self.r.render_device(u, self.my, tiles_ptr=self.tiles.data_ptr())
         with self.torch.cuda.stream(self.stream):
             self.dist.all_gather_into_tensor(self.gathered, self.tiles)
-        for rk, (first, step, count) in enumerate(self.parts):
-            if count == 0:
-                continue
-            p = Params.from_buffer_copy(bytes(self.my))
-            p.group_first, p.group_step, p.group_count = first, step, count
-            self.r.scatter_tiles_device(u, p, self.gathered[rk * self.max_count].data_ptr(), self.image.data_ptr())
+        self.r.scatter_gathered_device(u, self.my, self.world, self.max_count, self.gathered.data_ptr(), self.image.data_ptr())
         return self.image

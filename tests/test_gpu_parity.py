@@ -313,3 +313,31 @@ def test_full_size_frame_equals_oracle(mm, noise, scenes, renderer):
     assert img.tobytes() == ref.tobytes()
     for k in COUNTER_KEYS:
         assert cnt[k] == rcnt[k], k
+
+
+def test_scatter_gathered_single_launch(mm, noise, scenes, renderer):
+    """mm_scatter_gathered_device: the whole all-gather layout (world x max_count tiles, padded) in one launch."""
+    import torch
+
+    sc, u, p, ch = build_case(mm, "ragged", scenes)          # 84 groups: not a multiple of 8 -> padded rows
+    renderer.upload_scene(sc, noise)
+    full = renderer.render(u, p, ch)[0]
+    r2 = mm.Renderer(0)
+    r2.upload_scene(sc, noise)
+    r2.set_chunks(ch)
+    for world in (3, 8):
+        n_groups = p.grid_x * p.grid_y
+        parts = [mm.tile_partition(n_groups, r, world) for r in range(world)]
+        max_count = max(pt[2] for pt in parts)
+        gathered = torch.full((world * max_count, u.chunk_width ** 2, 4), 7.0, dtype=torch.float32, device="cuda:0")
+        torch.cuda.synchronize()
+        for rank, (first, step, count) in enumerate(parts):
+            q = mm.Params.from_buffer_copy(bytes(p))
+            q.group_first, q.group_step, q.group_count = first, step, count
+            r2.render_device(u, q, tiles_ptr=gathered[rank * max_count].data_ptr())
+        image = torch.zeros((int(u.view_height), int(u.view_width), 4), dtype=torch.float32, device="cuda:0")
+        torch.cuda.synchronize()
+        r2.scatter_gathered_device(u, p, world, max_count, gathered.data_ptr(), image.data_ptr())
+        r2.sync()
+        assert image.cpu().numpy().tobytes() == full.tobytes()
+    r2.close()
