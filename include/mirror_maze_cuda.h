@@ -56,7 +56,7 @@ typedef struct mm_chunk { uint32_t x, y; } mm_chunk;
  *
  * Virtual dispatch.  The kernel's RNG seed is a function of the Metal thread coordinates
  * (shaders.metal:298), so the Metal grid is part of the contract and is kept as a *virtual* grid:
- *   threads per group T = chunk_width^2 * spp,   dims = (min(32,T), T/min(32,T))   (execution width 32),
+ *   threads per group T = chunk_width^2 * spp (<= 32, or a multiple of 32),   dims = (min(32,T), T/min(32,T))   (execution width 32),
  *   grid = grid_x x grid_y groups,   group (tgid.x, tgid.y) renders chunk  chunks[tgid.x + tgid.y*grid_x]
  *   (shaders.metal:266 uses (width/2)/ppc as the row stride, which equals grid_x = 32 in the reference's
  *   only configuration; the stride is grid_x here),  flat = gid.x + dims.x*gid.y,  pixel = flat / spp,

@@ -203,6 +203,7 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
     if (chunk == 0 || chunk > 64) return fail(ctx, MM_ERR_UNSUPPORTED, "chunk_width must be in 1..64");
     const uint64_t T = (uint64_t)chunk * chunk * spp;
     if (T > (1u << 20)) return fail(ctx, MM_ERR_UNSUPPORTED, "chunk_width^2 * spp too large");
+    if (T > 32 && (T % 32) != 0) return fail(ctx, MM_ERR_UNSUPPORTED, "chunk_width^2 * spp must be <= 32 or a multiple of 32 (virtual threadgroup = 32 x T/32)");
     if (par->grid_x == 0 || par->grid_y == 0) return fail(ctx, MM_ERR_INVALID, "empty grid");
     const uint64_t n_groups = (uint64_t)par->grid_x * par->grid_y;
     if (n_groups != ctx->n_chunks) return fail(ctx, MM_ERR_INVALID, "grid_x*grid_y must equal the chunk count");

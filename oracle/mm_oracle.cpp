@@ -295,6 +295,7 @@ int validate(const mm_uniform *uni, const mm_params *p, uint32_t n_chunks, uint3
     if (chunk == 0 || chunk > 64) return MM_ERR_UNSUPPORTED;
     uint64_t T = (uint64_t)chunk * chunk * spp;
     if (T > (1u << 20)) return MM_ERR_UNSUPPORTED;
+    if (T > 32 && (T % 32) != 0) return MM_ERR_UNSUPPORTED;   // the virtual threadgroup is (32, T/32): Metal groups are rows of the execution width
     if (p->grid_x == 0 || p->grid_y == 0 || (uint64_t)p->grid_x * p->grid_y != n_chunks) return MM_ERR_INVALID;
     if (p->bounce_limit > 4096 || p->mirror_limit > 4096) return MM_ERR_INVALID;
     *T_out = (uint32_t)T;

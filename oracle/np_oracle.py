@@ -155,6 +155,7 @@ def _render(sc, noise, U_, P, chunks):
     ppc = chunk * chunk
     spp = int(P.spp)
     T = ppc * spp
+    assert T <= 32 or T % 32 == 0, "virtual threadgroup is (32, T/32)"
     dimx = min(32, T)
     dimy = T // dimx
     n_groups = P.grid_x * P.grid_y

@@ -22,6 +22,11 @@ CASES = {
     "chunk2_spp4": dict(maze=16, W=64, H=48, chunk=2, spp=4, bounce=6, mirror=15),
     "chunk8_spp2": dict(maze=10, W=64, H=64, chunk=8, spp=2, bounce=5, mirror=15),
     "chunk3_spp32": dict(maze=10, W=48, H=48, chunk=3, spp=32, bounce=5, mirror=15),
+    # odd virtual-dispatch shapes: 1 pixel x 256 samples per group; 25 pixels x 32 samples (T = 800, groups straddle
+    # blocks); 256 pixels x 1 sample
+    "chunk1_spp256": dict(maze=10, W=12, H=8, chunk=1, spp=256, bounce=5, mirror=15),
+    "chunk5_spp32": dict(maze=10, W=20, H=15, chunk=5, spp=32, bounce=5, mirror=15),
+    "chunk16_spp1": dict(maze=16, W=64, H=48, chunk=16, spp=1, bounce=6, mirror=15),
     # mirror_limit reached: break inside the mirror branch (shaders.metal:331-334)
     "mirror_limit2": dict(maze=32, W=96, H=64, chunk=4, spp=8, bounce=8, mirror=2, center=(-5.0, 0.0, 35.0), half_theta=2.4),
     # no bounces at all / one bounce
@@ -39,7 +44,7 @@ CASES = {
 }
 
 # cases small enough for the numpy transcription
-NP_CASES = ["cfg1", "yaw", "tiny_origin", "on_plane", "chunk2_spp4", "chunk8_spp2", "chunk3_spp32", "mirror_limit2", "bounce0", "bounce1", "all_miss", "ragged"]
+NP_CASES = ["cfg1", "yaw", "tiny_origin", "on_plane", "chunk1_spp256", "chunk5_spp32", "chunk16_spp1", "chunk2_spp4", "chunk8_spp2", "chunk3_spp32", "mirror_limit2", "bounce0", "bounce1", "all_miss", "ragged"]
 
 
 def build_case(mm, name, scenes=None):

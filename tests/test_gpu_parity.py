@@ -195,6 +195,10 @@ def test_error_codes(mm, noise, scenes):
     with pytest.raises(mm.MMError) as e:
         r.render(u, bad, ch)
     assert e.value.code == -5                                                    # MM_ERR_UNSUPPORTED
+    u5 = mm.default_uniform(10, 40, 30, 5)                                       # chunk 5, spp 2: T = 50 is not a (32, h) threadgroup
+    with pytest.raises(mm.MMError) as e:
+        r.render(u5, mm.full_frame_params(u5, spp=2, bounce_limit=2), mm.gen_chunks(40, 30, 5))
+    assert e.value.code == -5
     bad = mm.Params.from_buffer_copy(bytes(p)); bad.grid_x += 1
     with pytest.raises(mm.MMError) as e:
         r.render(u, bad, ch)

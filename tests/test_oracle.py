@@ -186,3 +186,11 @@ def test_ragged_frame_leaves_border_unwritten(mm, oracle, noise, scenes):
     sc, u, p, ch = build_case(mm, "ragged", scenes)
     img = oracle.render(sc, noise, u, p, ch)[0]
     assert (img[:, 48:, :] == 0).all() and (img[28:, :, :] == 0).all() and (img[:28, :48, 3] == 1).all()
+
+
+def test_oracle_rejects_ill_defined_dispatch_shapes(mm, oracle, noise, scenes):
+    """T = chunk^2 * spp must be <= 32 or a multiple of 32: the virtual threadgroup is (32, T/32) (main.rs:641-644)."""
+    sc = scenes(10)
+    u5 = mm.default_uniform(10, 40, 30, 5)
+    with pytest.raises(RuntimeError):
+        oracle.render(sc, noise, u5, mm.full_frame_params(u5, spp=2, bounce_limit=2), mm.gen_chunks(40, 30, 5))
