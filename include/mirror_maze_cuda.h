@@ -79,6 +79,8 @@ typedef struct mm_params {
 #define MM_FLAG_COUNTERS      1u   /* fill mm_counters beyond `rays` (slower kernel variant)          */
 #define MM_FLAG_FORCE_LITERAL 2u   /* use the literal-divide traversal for every ray (validation)     */
 #define MM_FLAG_FORCE_GLOBAL  4u   /* read BVH child pairs through L1 from global memory (the default) */
+#define MM_FLAG_MUX2         16u   /* experimental: two rays per lane, ray state in shared memory      */
+#define MM_FLAG_MUX3         32u   /* experimental: three rays per lane                                 */
 #define MM_FLAG_FORCE_SHARED  8u   /* stage BVH child pairs in shared memory when they fit twice per SM */
 
 /* Exact event counts of one render call; identical on CPU oracle and GPU (SURVEY §8 d). */

@@ -242,11 +242,18 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
     const size_t pair_bytes = (size_t)ctx->n_pairs * kPairSmemBytes;
     bool smem_nodes = ctx->n_pairs > 0 && !(par->flags & MM_FLAG_FORCE_GLOBAL) && pair_bytes <= smem_nodes_limit((par->flags & MM_FLAG_FORCE_SHARED) != 0) &&
                       red_bytes + pair_bytes <= ctx->smem_optin;
+    int mux = (par->flags & MM_FLAG_MUX3) ? 3 : ((par->flags & MM_FLAG_MUX2) ? 2 : 0);
+    if (const char *e = getenv("MM_MUX")) mux = atoi(e);                 // developer override
+    if (mux != 2 && mux != 3) mux = 0;
+    if (ctx->max_leaf > 30 || ctx->n_pairs == 0) mux = 0;                // descriptor bit budget of the K-rays-per-lane kernel
+    if (mux) smem_nodes = false;
     L.choice.smem_nodes = smem_nodes;
+    L.choice.mux = mux;
     L.choice.debug = debug;
     L.choice.counters = debug || (par->flags & MM_FLAG_COUNTERS);
-    L.smem = red_bytes + (smem_nodes ? pair_bytes : 0);
-    const uint64_t blocks = (p.total_paths + kBlockThreads - 1) / kBlockThreads;
+    const uint64_t paths_per_block = (uint64_t)kBlockThreads * (mux ? mux : 1);
+    L.smem = mux ? (size_t)6 * 16 * mux * kBlockThreads : red_bytes + (smem_nodes ? pair_bytes : 0);
+    const uint64_t blocks = (p.total_paths + paths_per_block - 1) / paths_per_block;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, MM_ERR_UNSUPPORTED, "too many paths for one launch");
     L.blocks = (unsigned)blocks;
     return MM_OK;

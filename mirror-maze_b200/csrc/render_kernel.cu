@@ -510,6 +510,8 @@ trace_kernel(const __grid_constant__ KParams P) {
     }
 }
 
+#include "trace_mux.cuh"
+
 // De-interleave gathered tiles into the frame (consumer side of the multi-GPU tile gather).
 __global__ void scatter_kernel(const float4 *__restrict__ tiles, float4 *__restrict__ image, const mm_chunk *__restrict__ chunks,
                                uint32_t group_first, uint32_t group_step, uint32_t group_count, uint32_t chunk, uint32_t ppc,
@@ -603,7 +605,12 @@ const void *kptr() { return reinterpret_cast<const void *>(&trace_kernel<S, C, D
 
 }  // namespace
 
+template <int K, bool C, bool D>
+const void *kptr_mux() { return reinterpret_cast<const void *>(&trace_kernel_mux<K, C, D>); }
+
 const void *kernel_ptr(KernelChoice c) {
+    if (c.mux == 2) return c.debug ? kptr_mux<2, true, true>() : (c.counters ? kptr_mux<2, true, false>() : kptr_mux<2, false, false>());
+    if (c.mux == 3) return c.debug ? kptr_mux<3, true, true>() : (c.counters ? kptr_mux<3, true, false>() : kptr_mux<3, false, false>());
     if (c.smem_nodes) {
         if (c.debug) return kptr<true, true, true>();
         return c.counters ? kptr<true, true, false>() : kptr<true, false, false>();

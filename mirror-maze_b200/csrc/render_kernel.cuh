@@ -81,7 +81,7 @@ struct KParams {
 constexpr int kBlockThreads = MM_BLOCK_THREADS;   // 32 warps/SM at <= 64 registers (measured best; profiles/r1_block_shape.txt)
 
 // Returns the kernel's static properties for the occupancy query and launch.
-struct KernelChoice { bool smem_nodes, counters, debug; };
+struct KernelChoice { bool smem_nodes, counters, debug; int mux; };   // mux: 0 = one ray per lane, 2 / 3 = trace_kernel_mux<K>
 const void *kernel_ptr(KernelChoice c);
 cudaError_t launch_trace(const KParams &p, KernelChoice c, unsigned blocks, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_scatter_all(const float *gathered, float *image, const mm_chunk *chunks, uint32_t world, uint32_t max_count,
