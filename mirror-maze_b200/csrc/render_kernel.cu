@@ -222,9 +222,12 @@ __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 or
 // for its own ray; only the interleaving between lanes changes.  (A plain while-while loop — all lanes descend to a
 // leaf, then all test — left 12 of 32 lanes active in the interior body; see profiles/.)
 // `lit` lanes (operands outside the guarded ranges, or MM_FLAG_FORCE_LITERAL) use the literal-divide slab test.
-constexpr uint32_t kLeafWeight = 3;   // measured best on B200 (profiles/r1_sched_sweep.txt)
+#ifndef MM_LEAF_WEIGHT
+#define MM_LEAF_WEIGHT 4
+#endif
+constexpr uint32_t kLeafWeight = MM_LEAF_WEIGHT;   // measured best on B200 (profiles/r1_sched_sweep.txt)
 #ifndef MM_INNER_REPS
-#define MM_INNER_REPS 3
+#define MM_INNER_REPS 4
 #endif
 constexpr uint32_t kInnerReps = MM_INNER_REPS;
 
