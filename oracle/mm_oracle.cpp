@@ -131,7 +131,12 @@ inline void intersect_bvh_iterative(Ray &beam, const Scene &sc, Counts &c) {
     uint32_t head = 0;
     uint32_t run = 0;
     c.rays++;
-    if (c.trace) c.trace->push_back((uint16_t)(0xFFF0u | (beam.dir.x < 0.0f ? 1u : 0u) | (beam.dir.y < 0.0f ? 2u : 0u) | (beam.dir.z < 0.0f ? 4u : 0u)));
+    if (c.trace) {   // segment header: 0xFFF0 | octant, then |dir.y| / |dir| quantised to 0..255 (a cheap predictor of traversal length)
+        c.trace->push_back((uint16_t)(0xFFF0u | (beam.dir.x < 0.0f ? 1u : 0u) | (beam.dir.y < 0.0f ? 2u : 0u) | (beam.dir.z < 0.0f ? 4u : 0u)));
+        float l = std::sqrt(beam.dir.x * beam.dir.x + beam.dir.y * beam.dir.y + beam.dir.z * beam.dir.z);
+        float q = l > 0.0f ? std::fabs(beam.dir.y) / l * 255.0f : 0.0f;
+        c.trace->push_back((uint16_t)(q < 0.0f ? 0.0f : (q > 255.0f ? 255.0f : q)));
+    }
     while (true) {
         const mm_bvh_node &nd = sc.nodes[node];
         if (nd.tri_count > 0) {

@@ -44,7 +44,7 @@ def get_traces(maze=32, W=1920, H=1080, spp=16, bounces=8, every=97):
             octants.append(octs); octs = []
             continue
         if (tok & 0xFFF8) == 0xFFF0:
-            octs.append(tok & 7)
+            octs.append((tok & 7, next(it)))      # (octant, |dir.y|/|dir| in 0..255)
             continue
         nxt = next(it)
         if nxt == 0xFFFF:

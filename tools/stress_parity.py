@@ -1,0 +1,39 @@
+"""Developer tool (GPU box): many seeded random camera poses, GPU against the CPU oracle, every observable bit for bit."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import mirror_maze_b200 as mm
+from oracle import oracle
+
+def main():
+    n_poses = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    noise = mm.load_noise()
+    r = mm.Renderer(0)
+    rng = np.random.default_rng(2026)
+    bad = rays = lit = 0
+    t0 = time.time()
+    for maze in (10, 32, 64, 128):
+        sc = mm.MazeScene(maze, 0)
+        r.upload_scene(sc, noise)
+        ch = mm.gen_chunks(96, 64, 4)
+        for i in range(n_poses // 4):
+            cell = rng.integers(0, maze, size=2)
+            half = 5.0 * maze
+            center = (-half + 10.0 * cell[0] + float(rng.uniform(0.5, 9.5)), float(rng.uniform(-7.5, 1.9)), -half + 10.0 * cell[1] + float(rng.uniform(0.5, 9.5)))
+            if i % 7 == 0:
+                center = (-half + 10.0 * cell[0], center[1], center[2])            # exactly on a wall-plane coordinate
+            u = mm.default_uniform(maze, 96, 64, 4, time=int(rng.integers(0, 100000)), camera_center=center, half_theta=float(rng.uniform(0.0, np.pi)))
+            p = mm.full_frame_params(u, spp=int(rng.choice([1, 4, 8, 16])), bounce_limit=int(rng.integers(1, 12)), mirror_limit=int(rng.choice([2, 15])), flags=mm.FLAG_COUNTERS)
+            img, cnt, dbg = r.render(u, p, ch, debug=True)
+            rimg, rcnt, rdbg = oracle.render(sc, noise, u, p, ch, debug=True)
+            ok = img.tobytes() == rimg.tobytes() and all(dbg[k].tobytes() == rdbg[k].tobytes() for k in dbg) and \
+                all(cnt[k] == rcnt[k] for k in ("paths", "rays", "inner_visits", "leaf_visits", "rect_tests", "hits", "max_stack"))
+            bad += 0 if ok else 1
+            rays += cnt["rays"]; lit += cnt["literal_rays"]
+            if not ok:
+                print("MISMATCH maze", maze, "pose", i, center)
+    print(f"stress parity: {n_poses} poses over mazes 10/32/64/128, {rays} rays ({lit} on the literal-divide path), mismatches: {bad}, {time.time() - t0:.1f} s")
+    return 1 if bad else 0
+
+if __name__ == "__main__":
+    sys.exit(main())
