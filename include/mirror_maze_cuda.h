@@ -81,6 +81,10 @@ typedef struct mm_params {
 #define MM_FLAG_FORCE_GLOBAL  4u   /* read BVH child pairs through L1 from global memory (the default) */
 #define MM_FLAG_MUX2         16u   /* experimental: two rays per lane, ray state in shared memory      */
 #define MM_FLAG_MUX3         32u   /* experimental: three rays per lane                                 */
+#define MM_FLAG_RCP_SLAB     64u   /* opt-in arithmetic variant: slab quotients (b - o) * RN(1/d) instead of the literal
+                                      (b - o) / d of shaders.metal:88-93 — what a fast-math compile of the shader amounts to.
+                                      NOT the default; the oracle implements the same rule under the same flag and the
+                                      kernel matches it bit for bit, but results differ from the literal mode's.       */
 #define MM_FLAG_FORCE_SHARED  8u   /* stage BVH child pairs in shared memory when they fit twice per SM */
 
 /* Exact event counts of one render call; identical on CPU oracle and GPU (SURVEY §8 d). */

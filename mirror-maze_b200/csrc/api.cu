@@ -232,6 +232,7 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
     p.root_link = ctx->root_link; p.root_count = ctx->root_count;
     p.noise_w = ctx->noise_w; p.noise_h = ctx->noise_h;
     p.force_literal = (par->flags & MM_FLAG_FORCE_LITERAL) ? 1u : 0u;
+    p.rcp_mode = (par->flags & MM_FLAG_RCP_SLAB) ? 1u : 0u;
     p.scene_fast_ok = ctx->fast_ok ? 1u : 0u;
     p.total_paths = (uint64_t)count * T;
     p.pairs = ctx->d_pairs; p.rects = ctx->d_rects; p.shade = ctx->d_shade;
@@ -245,7 +246,7 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
     int mux = (par->flags & MM_FLAG_MUX3) ? 3 : ((par->flags & MM_FLAG_MUX2) ? 2 : 0);
     if (const char *e = getenv("MM_MUX")) mux = atoi(e);                 // developer override
     if (mux != 2 && mux != 3) mux = 0;
-    if (ctx->max_leaf > 30 || ctx->n_pairs == 0) mux = 0;                // descriptor bit budget of the K-rays-per-lane kernel
+    if (ctx->max_leaf > 30 || ctx->n_pairs == 0 || (par->flags & MM_FLAG_RCP_SLAB)) mux = 0;                // descriptor bit budget of the K-rays-per-lane kernel
     if (mux) smem_nodes = false;
     L.choice.smem_nodes = smem_nodes;
     L.choice.mux = mux;

@@ -73,9 +73,12 @@ __device__ __forceinline__ V3 quat_mult(V3 vec, Q4 q) {
 
 struct Axis { float o, d, r, rl; };
 
-template <bool FAST>
+// RCP (MM_FLAG_RCP_SLAB): the opt-in reciprocal-multiply slab arithmetic t = (b - o) * RN(1/d) — what a fast-math compile
+// of the reference's divide amounts to; the oracle implements the same rule under the same flag.
+template <bool FAST, bool RCP = false>
 __device__ __forceinline__ float quot(float b, const Axis &a) {
     float x = fsub(b, a.o);
+    if (RCP) return fmul(x, a.r);
     if (FAST) {
         float p = fmul(x, a.rl);
         float q1 = __fmaf_rn(x, a.r, p);
@@ -91,6 +94,13 @@ __device__ __forceinline__ bool axis_safe(float o, float d) {
     bool dok = ad >= 8.673617379884035e-19f /*2^-60*/ && ad <= 1.152921504606847e18f /*2^60*/;
     bool ook = ao == 0.0f || (ao >= 9.094947017729282e-13f /*2^-40*/ && ao <= 1073741824.0f /*2^30*/);
     return dok && ook;
+}
+
+// Reciprocal-multiply mode: the travel-ordered form needs finite operands and a finite non-zero reciprocal (no NaN from
+// 0 * inf, monotone products); anything else takes the general min/max form.
+__device__ __forceinline__ bool rcp_safe(float o, float d) {
+    const float ad = fabsf(d);
+    return ad >= 1.1754943508222875e-38f /*2^-126*/ && ad <= 8.507059173023462e37f /*2^126*/ && fabsf(o) <= 3.4028234663852886e38f;
 }
 
 struct Tally { uint32_t inner, leaf, rect, max_stack; };
@@ -150,28 +160,28 @@ constexpr uint32_t CUR_END = 0xFFFFFFFFu;   // traversal finished
 // The literal `dist` values are never materialised: with hit_k = (tmax_k >= tmin_k && tmin_k < t && tmax_k > 0) and
 // dist_k = hit_k ? tmin_k : 1e30 (tmin_k < t <= 1e30 when hit), `dist1 > dist2` is hit2 && (!hit1 || tmin1 > tmin2),
 // `dist_near == 1e30` is !hit1 && !hit2 and `dist_far != 1e30` is hit1 && hit2 — the same decisions, fewer instructions.
-template <bool FAST, bool CNT>
+template <bool FAST, bool CNT, bool RCP = false>
 __device__ __forceinline__ void inner_step(const float4 &bx, const float4 &by, const float4 &bz, const uint2 &lk, const Axis &ax,
                                            const Axis &ay, const Axis &az, float t, uint32_t &cur, uint32_t &head, uint32_t *stack,
                                            Tally &tl) {
     float lo1, hi1, lo2, hi2;
     if (FAST) {
-        lo1 = fmaxf(fmaxf(quot<true>(bx.x, ax), quot<true>(by.x, ay)), quot<true>(bz.x, az));
-        hi1 = fminf(fminf(quot<true>(bx.y, ax), quot<true>(by.y, ay)), quot<true>(bz.y, az));
-        lo2 = fmaxf(fmaxf(quot<true>(bx.z, ax), quot<true>(by.z, ay)), quot<true>(bz.z, az));
-        hi2 = fminf(fminf(quot<true>(bx.w, ax), quot<true>(by.w, ay)), quot<true>(bz.w, az));
+        lo1 = fmaxf(fmaxf(quot<true, RCP>(bx.x, ax), quot<true, RCP>(by.x, ay)), quot<true, RCP>(bz.x, az));
+        hi1 = fminf(fminf(quot<true, RCP>(bx.y, ax), quot<true, RCP>(by.y, ay)), quot<true, RCP>(bz.y, az));
+        lo2 = fmaxf(fmaxf(quot<true, RCP>(bx.z, ax), quot<true, RCP>(by.z, ay)), quot<true, RCP>(bz.z, az));
+        hi2 = fminf(fminf(quot<true, RCP>(bx.w, ax), quot<true, RCP>(by.w, ay)), quot<true, RCP>(bz.w, az));
     } else {
-        float t1 = quot<false>(bx.x, ax), t2 = quot<false>(bx.y, ax);
+        float t1 = quot<false, RCP>(bx.x, ax), t2 = quot<false, RCP>(bx.y, ax);
         lo1 = fminf(t1, t2); hi1 = fmaxf(t1, t2);
-        t1 = quot<false>(by.x, ay); t2 = quot<false>(by.y, ay);
+        t1 = quot<false, RCP>(by.x, ay); t2 = quot<false, RCP>(by.y, ay);
         lo1 = fmaxf(lo1, fminf(t1, t2)); hi1 = fminf(hi1, fmaxf(t1, t2));
-        t1 = quot<false>(bz.x, az); t2 = quot<false>(bz.y, az);
+        t1 = quot<false, RCP>(bz.x, az); t2 = quot<false, RCP>(bz.y, az);
         lo1 = fmaxf(lo1, fminf(t1, t2)); hi1 = fminf(hi1, fmaxf(t1, t2));
-        t1 = quot<false>(bx.z, ax); t2 = quot<false>(bx.w, ax);
+        t1 = quot<false, RCP>(bx.z, ax); t2 = quot<false, RCP>(bx.w, ax);
         lo2 = fminf(t1, t2); hi2 = fmaxf(t1, t2);
-        t1 = quot<false>(by.z, ay); t2 = quot<false>(by.w, ay);
+        t1 = quot<false, RCP>(by.z, ay); t2 = quot<false, RCP>(by.w, ay);
         lo2 = fmaxf(lo2, fminf(t1, t2)); hi2 = fminf(hi2, fmaxf(t1, t2));
-        t1 = quot<false>(bz.z, az); t2 = quot<false>(bz.w, az);
+        t1 = quot<false, RCP>(bz.z, az); t2 = quot<false, RCP>(bz.w, az);
         lo2 = fmaxf(lo2, fminf(t1, t2)); hi2 = fminf(hi2, fmaxf(t1, t2));
     }
     const bool hit1 = (hi1 >= lo1) & (lo1 < t) & (hi1 > 0.0f);          // :94
@@ -242,7 +252,7 @@ struct Hit { float t; uint32_t slot; };
 #else
 #define MM_TRAVERSE_ATTR __forceinline__
 #endif
-template <bool MIXED, bool SMEM, bool CNT>
+template <bool MIXED, bool SMEM, bool CNT, bool RCP = false>
 __device__ MM_TRAVERSE_ATTR Hit traverse(PairView<SMEM> pv, const RectI *__restrict__ rects, uint32_t root, bool alive, bool lit,
                                          V3 ori, V3 dir, float beam_t, uint32_t beam_slot, uint32_t *stack, Tally *tlp) {
     Tally tl = {0u, 0u, 0u, 0u};
@@ -272,8 +282,8 @@ __device__ MM_TRAVERSE_ATTR Hit traverse(PairView<SMEM> pv, const RectI *__restr
                     uint2 lk;
                     rp.load(cur, bx, by, bz, lk);
                     if (CNT) tl.inner++;
-                    if (!MIXED || !lit) inner_step<true, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
-                    else inner_step<false, CNT>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
+                    if (!MIXED || !lit) inner_step<true, CNT, RCP>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
+                    else inner_step<false, CNT, RCP>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
                 }
             }
         } else {
@@ -393,11 +403,19 @@ trace_kernel(const __grid_constant__ KParams P) {
         int n = 0;
         bool alive = active && n_alive;
         while (__any_sync(0xFFFFFFFFu, alive)) {
+            // lit: this ray must use the general slab form (operands outside the guarded ranges / flags)
             const bool lit = P.force_literal || !P.scene_fast_ok ||
-                             !(axis_safe(ori.x, dir.x) && axis_safe(ori.y, dir.y) && axis_safe(ori.z, dir.z));
+                             !(P.rcp_mode ? (rcp_safe(ori.x, dir.x) && rcp_safe(ori.y, dir.y) && rcp_safe(ori.z, dir.z))
+                                          : (axis_safe(ori.x, dir.x) && axis_safe(ori.y, dir.y) && axis_safe(ori.z, dir.z)));
+            const bool any_lit = __any_sync(0xFFFFFFFFu, alive && lit);
             Hit h;
-            if (!__any_sync(0xFFFFFFFFu, alive && lit)) h = traverse<false, SMEM_NODES, CNT>(pv, P.rects, root, alive, false, ori, dir, t, slot, stack, &tl);
-            else h = traverse<true, SMEM_NODES, CNT>(pv, P.rects, root, alive, lit, ori, dir, t, slot, stack, &tl);
+            if (P.rcp_mode) {
+                if (!any_lit) h = traverse<false, SMEM_NODES, CNT, true>(pv, P.rects, root, alive, false, ori, dir, t, slot, stack, &tl);
+                else h = traverse<true, SMEM_NODES, CNT, true>(pv, P.rects, root, alive, lit, ori, dir, t, slot, stack, &tl);
+            } else {
+                if (!any_lit) h = traverse<false, SMEM_NODES, CNT>(pv, P.rects, root, alive, false, ori, dir, t, slot, stack, &tl);
+                else h = traverse<true, SMEM_NODES, CNT>(pv, P.rects, root, alive, lit, ori, dir, t, slot, stack, &tl);
+            }
             t = h.t; slot = h.slot;
             if (alive) {
                 if (lit) nliteral++;

@@ -58,6 +58,7 @@ struct KParams {
     uint32_t root_link, root_count;   // descriptor of node 0 (pair 0 unless the root is a leaf)
     uint32_t noise_w, noise_h;
     uint32_t force_literal;
+    uint32_t rcp_mode;         // MM_FLAG_RCP_SLAB: slab quotients as (b - o) * RN(1/d)
     uint32_t scene_fast_ok;
     uint64_t total_paths;
     const PairRec *pairs;

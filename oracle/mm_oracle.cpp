@@ -70,6 +70,7 @@ struct Scene {
 
 struct Counts {
     uint64_t rays = 0, inner = 0, leaf = 0, rect = 0, hits = 0, max_stack = 0; bool overflow = false;
+    bool rcp = false;                          // MM_FLAG_RCP_SLAB
     std::vector<uint16_t> *trace = nullptr;   // optional event trace for scheduling studies (tools/sched_sim.py)
 };
 
@@ -104,6 +105,19 @@ inline float intersect_aabb(const Ray &beam, f3 bmin, f3 bmax) {
     float ty1 = (bmin.y - beam.ori.y) / beam.dir.y, ty2 = (bmax.y - beam.ori.y) / beam.dir.y;
     tmin = fmax_c(tmin, fmin_c(ty1, ty2)); tmax = fmin_c(tmax, fmax_c(ty1, ty2));
     float tz1 = (bmin.z - beam.ori.z) / beam.dir.z, tz2 = (bmax.z - beam.ori.z) / beam.dir.z;
+    tmin = fmax_c(tmin, fmin_c(tz1, tz2)); tmax = fmin_c(tmax, fmax_c(tz1, tz2));
+    if (tmax >= tmin && tmin < beam.t && tmax > 0.0f) return tmin; else return 1e30f;
+}
+
+// Opt-in variant (MM_FLAG_RCP_SLAB): the same test with t = (b - o) * (1/d), one IEEE reciprocal per axis — what a
+// fast-math compile of :88-93 amounts to.  Not the default; only used when the caller asks for it.
+inline float intersect_aabb_rcp(const Ray &beam, f3 bmin, f3 bmax) {
+    float ix = 1.0f / beam.dir.x, iy = 1.0f / beam.dir.y, iz = 1.0f / beam.dir.z;
+    float tx1 = (bmin.x - beam.ori.x) * ix, tx2 = (bmax.x - beam.ori.x) * ix;
+    float tmin = fmin_c(tx1, tx2), tmax = fmax_c(tx1, tx2);
+    float ty1 = (bmin.y - beam.ori.y) * iy, ty2 = (bmax.y - beam.ori.y) * iy;
+    tmin = fmax_c(tmin, fmin_c(ty1, ty2)); tmax = fmin_c(tmax, fmax_c(ty1, ty2));
+    float tz1 = (bmin.z - beam.ori.z) * iz, tz2 = (bmax.z - beam.ori.z) * iz;
     tmin = fmax_c(tmin, fmin_c(tz1, tz2)); tmax = fmin_c(tmax, fmax_c(tz1, tz2));
     if (tmax >= tmin && tmin < beam.t && tmax > 0.0f) return tmin; else return 1e30f;
 }
@@ -153,8 +167,10 @@ inline void intersect_bvh_iterative(Ray &beam, const Scene &sc, Counts &c) {
         c.inner++;
         run++;
         uint32_t left = nd.left_first, right = nd.left_first + 1;
-        float dist1 = intersect_aabb(beam, ld(sc.nodes[left].aabb_min), ld(sc.nodes[left].aabb_max));
-        float dist2 = intersect_aabb(beam, ld(sc.nodes[right].aabb_min), ld(sc.nodes[right].aabb_max));
+        float dist1 = c.rcp ? intersect_aabb_rcp(beam, ld(sc.nodes[left].aabb_min), ld(sc.nodes[left].aabb_max))
+                            : intersect_aabb(beam, ld(sc.nodes[left].aabb_min), ld(sc.nodes[left].aabb_max));
+        float dist2 = c.rcp ? intersect_aabb_rcp(beam, ld(sc.nodes[right].aabb_min), ld(sc.nodes[right].aabb_max))
+                            : intersect_aabb(beam, ld(sc.nodes[right].aabb_min), ld(sc.nodes[right].aabb_max));
         if (dist1 > dist2) {
             float temp = dist1; dist1 = dist2; dist2 = temp;
             uint32_t nemp = left; left = right; right = nemp;
@@ -341,6 +357,7 @@ int mmo_render(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *nod
 #pragma omp parallel
     {
         Counts c;
+        c.rcp = (params->flags & MM_FLAG_RCP_SLAB) != 0;
         std::vector<f3> test(T);
         std::vector<uint32_t> pix(2 * (size_t)T);
 #pragma omp for schedule(dynamic, 8)

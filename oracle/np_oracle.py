@@ -51,8 +51,21 @@ def _random(state):
     return state, result.astype(F) / F(4294967296.0)
 
 
+RCP_SLAB = False   # set by render() from params.flags & 64 (MM_FLAG_RCP_SLAB): t = (b - o) * (1/d) instead of (b - o) / d
+
+
 def _aabb(o, d, t, bmin, bmax):
     """shaders.metal:87-95, vectorised."""
+    if RCP_SLAB:
+        i = [F(1.0) / d[0], F(1.0) / d[1], F(1.0) / d[2]]
+        tx1 = (bmin[0] - o[0]) * i[0]; tx2 = (bmax[0] - o[0]) * i[0]
+        tmin = np.fmin(tx1, tx2); tmax = np.fmax(tx1, tx2)
+        ty1 = (bmin[1] - o[1]) * i[1]; ty2 = (bmax[1] - o[1]) * i[1]
+        tmin = np.fmax(tmin, np.fmin(ty1, ty2)); tmax = np.fmin(tmax, np.fmax(ty1, ty2))
+        tz1 = (bmin[2] - o[2]) * i[2]; tz2 = (bmax[2] - o[2]) * i[2]
+        tmin = np.fmax(tmin, np.fmin(tz1, tz2)); tmax = np.fmin(tmax, np.fmax(tz1, tz2))
+        ok = (tmax >= tmin) & (tmin < t) & (tmax > 0)
+        return np.where(ok, tmin, F(1e30)).astype(F)
     tx1 = (bmin[0] - o[0]) / d[0]; tx2 = (bmax[0] - o[0]) / d[0]
     tmin = np.fmin(tx1, tx2); tmax = np.fmax(tx1, tx2)
     ty1 = (bmin[1] - o[1]) / d[1]; ty2 = (bmax[1] - o[1]) / d[1]
@@ -145,8 +158,13 @@ def _traverse(sc, o, d, t, index, counters):
 
 def render(scene, noise, uniform, params, chunks):
     """Full-grid render (group_first/step/count are honoured).  Returns (image, counters, debug)."""
-    with np.errstate(all="ignore"):
-        return _render(scene, noise, uniform, params, chunks)
+    global RCP_SLAB
+    RCP_SLAB = bool(params.flags & 64)
+    try:
+        with np.errstate(all="ignore"):
+            return _render(scene, noise, uniform, params, chunks)
+    finally:
+        RCP_SLAB = False
 
 
 def _render(sc, noise, U_, P, chunks):

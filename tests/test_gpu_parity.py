@@ -346,3 +346,15 @@ def test_scatter_gathered_single_launch(mm, noise, scenes, renderer):
         r2.sync()
         assert image.cpu().numpy().tobytes() == full.tobytes()
     r2.close()
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2_small", "maze64", "yaw", "on_plane", "tiny_origin", "mirror_limit2", "maze256"])
+def test_rcp_slab_variant_matches_oracle(mm, oracle, noise, scenes, renderer, name):
+    """MM_FLAG_RCP_SLAB: the opt-in reciprocal-multiply slab arithmetic, bit for bit against the oracle in the same mode."""
+    sc, u, p, ch = build_case(mm, name, scenes)
+    renderer.upload_scene(sc, noise)
+    p.flags = mm.FLAG_RCP_SLAB
+    ref = oracle.render(sc, noise, u, p, ch, debug=True)
+    assert_same(renderer.render(u, p, ch, debug=True), ref)
+    p.flags = mm.FLAG_RCP_SLAB | mm.FLAG_FORCE_LITERAL          # general min/max form for every ray
+    assert_same(renderer.render(u, p, ch, debug=True), ref)
