@@ -119,7 +119,7 @@ def cpu_reference_run(a, steps, warmup, threads=0):
     scene = mm.MazeScene(a.maze, 0)
     u = mm.default_uniform(a.maze, a.width, a.height, 4)
     chunks = mm.gen_chunks(a.width, a.height, 4)
-    p = mm.full_frame_params(u, spp=a.spp, bounce_limit=a.bounces, mirror_limit=a.mirror_limit)
+    p = mm.full_frame_params(u, spp=a.spp, bounce_limit=a.bounces, mirror_limit=a.mirror_limit, flags=a.flags & 64)   # same arithmetic mode
     n_groups = p.grid_x * p.grid_y
     p.group_first, p.group_step = 0, max(1, a.cpu_crop)
     p.group_count = (n_groups + p.group_step - 1) // p.group_step
@@ -328,7 +328,8 @@ def run_ours(a):
                        "parallelism": f"image tiles x{world} (interleaved 4x4-chunk groups), scene replicated" + (", NCCL all-gather" if world > 1 else ""),
                        "l2_flush": "256 MiB device fill between timed iterations", "nodes_in_shared": info["nodes_in_shared"],
                        "blocks_per_sm": info["blocks_per_sm"], "bvh_nodes": info["n_nodes"], "planes": info["n_planes"],
-                       "literal_rays_per_frame": cnt_frame["literal_rays"]},
+                       "literal_rays_per_frame": cnt_frame["literal_rays"],
+                       "arithmetic": "opt-in (b-o)*RN(1/d) slab quotients (MM_FLAG_RCP_SLAB)" if (a.flags & 64) else "IEEE fp32, slab quotients bit-identical to the literal (b-o)/d"},
             "clocks": clocks, "roofline": roofline,
             "e2e": {"value": round(e2e_rays / e2e_s / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": round(1e3 * e2e_s / e2e_steps, 4), "steps": e2e_steps,
