@@ -305,6 +305,12 @@ def run_ours(a):
     issue_peak_max = info["n_sms"] * 128 * sm_max * 1e6 / 1e12            # T lane-ops/s at max clock
     issue_peak_now = info["n_sms"] * 128 * sm_now * 1e6 / 1e12            # at the clock seen under load
     achieved_tops = ops_per_launch / (kernel_mean_ms * 1e-3) / 1e12 if kernel_mean_ms else 0.0
+    # measured peaks of the two binding rooflines (micro-benchmarks in the library; untimed, after the measurement)
+    pair_table_bytes = max(128, (info["n_nodes"] - 1) // 2 * 128)
+    gather_peak = r.microbench(0, pair_table_bytes)            # GB/s of the per-visit fetch pattern from a table of the scene's size
+    ffma_peak = r.microbench(1)                                # T FP32 FMA lane-instr/s
+    node_bytes = (64 * cnt_frame["inner_visits"] + 52 * cnt_frame["rect_tests"]) / world
+    node_gbs = node_bytes / (kernel_mean_ms * 1e-3) / 1e9 if kernel_mean_ms else 0.0
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -316,7 +322,12 @@ def run_ours(a):
                 "algorithmic_bytes_per_launch": int(bytes_per_launch),
                 "note": "scene is on-chip (smem/L1/L2): algorithmic node+primitive bytes are served by shared memory, not HBM; "
                         "the binding limit is FP32 issue, reported in fp32_issue",
+                "node_fetch": {"achieved": round(node_gbs, 1), "peak": round(gather_peak, 1), "unit": "GB/s", "frac": round(node_gbs / gather_peak, 4) if gather_peak else None,
+                               "def": "algorithmic node+primitive bytes (64 B per inner visit + 52 B per rect test) over the kernel time, against the "
+                                      "measured rate of the same fetch pattern (3 x 16 B + 8 B from random 128-B records) on a table of the scene's size "
+                                      f"({pair_table_bytes} B, mm_microbench)"},
                 "fp32_issue": {"achieved": round(achieved_tops, 3), "peak": round(issue_peak_max, 2), "peak_at_load_clock": round(issue_peak_now, 2),
+                               "peak_measured_ffma": round(ffma_peak, 2),
                                "unit": "T lane-op/s", "frac": round(achieved_tops / issue_peak_max, 4),
                                "frac_at_load_clock": round(achieved_tops / issue_peak_now, 4),
                                "algorithmic_ops_per_launch": int(ops_per_launch),

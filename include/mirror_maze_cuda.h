@@ -211,6 +211,17 @@ int mm_present(mm_ctx *ctx, float *out_rgba);
 int mm_present_blur_device(mm_ctx *ctx, const float *d_src, float *d_dst, uint32_t width, uint32_t height);
 
 /*
+ * Micro-benchmarks behind the rooflines of this path (SURVEY §8 d; neither is in MEASURED_PEAKS.json):
+ *   MM_MICROBENCH_GATHER  GB/s of useful bytes when every lane fetches the traversal's per-visit pattern (three 16-B
+ *                         loads + one 8-B load = 56 B) from random 128-B records of a table of `table_bytes`
+ *                         (pass the scene's pair-table size: L1-resident at 32x32, L2-resident at 256x256);
+ *   MM_MICROBENCH_FFMA    T lane-instructions/s of dependent-chain-free FP32 FMAs (table_bytes ignored).
+ */
+#define MM_MICROBENCH_GATHER 0
+#define MM_MICROBENCH_FFMA   1
+int mm_microbench(mm_ctx *ctx, int kind, uint64_t table_bytes, double *result);
+
+/*
  * Self-test of the kernel's shared-reciprocal slab quotient (see render_kernel.cu header): evaluates n_pairs
  * pseudo-random (x, d) pairs inside the guarded ranges, half of them adjacent to rounding midpoints, with both
  * the fast sequence and __fdiv_rn, and returns how many differ (must be 0).

@@ -115,6 +115,7 @@ PROTOTYPES = {
     "mm_stream": (C.c_int, [_vp, _P(_vp)]),
     "mm_get_scene_info": (C.c_int, [_vp, _P(SceneInfo)]),
     "mm_selftest_quotient": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _P(C.c_uint64)]),
+    "mm_microbench": (C.c_int, [_vp, C.c_int, C.c_uint64, _P(C.c_double)]),
     "mm_present": (C.c_int, [_vp, _vp]),
     "mm_present_blur_device": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32]),
     "mm_move_camera": (C.c_int, [_vp, C.c_uint32, Float3, Float4, _vp, C.c_uint32, C.c_float, _P(Float3)]),

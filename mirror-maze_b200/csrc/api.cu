@@ -428,6 +428,45 @@ int mm_present(mm_ctx *ctx, float *out_rgba) {
     return MM_OK;
 }
 
+int mm_microbench(mm_ctx *ctx, int kind, uint64_t table_bytes, double *result) {
+    if (!ctx || !result) return MM_ERR_INVALID;
+    ctx->err.clear();
+    CK(cudaSetDevice(ctx->device));
+    const unsigned blocks = (unsigned)ctx->n_sms * 8u;
+    float *sink = reinterpret_cast<float *>(ctx->d_counters);
+    float ms = 0.0f;
+    if (kind == MM_MICROBENCH_GATHER) {
+        if (table_bytes < 128) return fail(ctx, MM_ERR_INVALID, "mm_microbench: table smaller than one record");
+        const uint32_t n_records = (uint32_t)(table_bytes / 128 > 0x7FFFFFFFull ? 0x7FFFFFFFull : table_bytes / 128);
+        void *table = nullptr;
+        CK(cudaMalloc(&table, (size_t)n_records * 128));
+        cudaError_t e = cudaMemsetAsync(table, 0, (size_t)n_records * 128, ctx->stream);
+        const uint32_t iters = 4096;
+        if (e == cudaSuccess) e = launch_mb_gather(table, n_records, 256, blocks, sink, ctx->stream);      // warm-up
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev0, ctx->stream);
+        if (e == cudaSuccess) e = launch_mb_gather(table, n_records, iters, blocks, sink, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev1, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(ctx->ev1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        cudaFree(table);
+        if (e != cudaSuccess) return fail(ctx, MM_ERR_CUDA, std::string("mm_microbench: ") + cudaGetErrorString(e));
+        *result = (double)blocks * 256.0 * iters * 56.0 / (ms * 1e-3) / 1e9;            // GB/s of useful bytes
+    } else if (kind == MM_MICROBENCH_FFMA) {
+        const uint32_t iters = 1u << 16;
+        CK(launch_mb_ffma(1024, blocks, sink, ctx->stream));
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        CK(launch_mb_ffma(iters, blocks, sink, ctx->stream));
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        *result = (double)blocks * 256.0 * iters * 8.0 / (ms * 1e-3) / 1e12;             // T lane-instructions/s
+    } else {
+        return fail(ctx, MM_ERR_INVALID, "mm_microbench: unknown kind");
+    }
+    ctx->timed = false;
+    return MM_OK;
+}
+
 int mm_selftest_quotient(mm_ctx *ctx, uint64_t n_pairs, uint64_t seed, uint64_t *mismatches) {
     if (!ctx || !mismatches) return MM_ERR_INVALID;
     ctx->err.clear();

@@ -621,6 +621,34 @@ __global__ void __launch_bounds__(256) blur_kernel(const float4 *__restrict__ sr
     dst[row + x] = o;
 }
 
+// Micro-benchmarks for the two rooflines the path is measured against (SURVEY §8 d): how fast can this GPU fetch 56 useful
+// bytes (three 16-B loads + one 8-B load, the traversal's per-visit pattern) from random 128-B records of a table of the
+// scene's size, and how fast can it issue FP32 FMAs.  Independent addresses / chains: these are peaks, not models.
+__global__ void __launch_bounds__(256) mb_gather_kernel(const float4 *__restrict__ table, uint32_t n_records, uint32_t iters,
+                                                        float *__restrict__ sink) {
+    uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
+    float acc = 0.0f;
+    for (uint32_t i = 0; i < iters; i++) {
+        idx = idx * 747796405u + 2891336453u;
+        const float4 *rec = table + (size_t)((idx >> 8) % n_records) * 8;
+        const uint32_t down = (idx & 1u) * 4u;                                  // either travel order, like the kernel
+        const float4 a = __ldg(rec + down), b = __ldg(rec + 1 + down), c = __ldg(rec + 2 + down);
+        const float2 l = __ldg(reinterpret_cast<const float2 *>(rec + 3));
+        acc += a.x + a.w + b.y + c.z + l.x;
+    }
+    if (acc == 12345.678f) sink[0] = acc;                                       // keep the loads alive
+}
+__global__ void __launch_bounds__(256) mb_ffma_kernel(uint32_t iters, float *__restrict__ sink) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.0f, a2 = a0 + 2.0f, a3 = a0 + 3.0f, a4 = a0 + 4.0f, a5 = a0 + 5.0f, a6 = a0 + 6.0f, a7 = a0 + 7.0f;
+    const float m = 1.000001f, c = 1e-7f;
+    for (uint32_t i = 0; i < iters; i++) {
+        a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
+        a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
+    }
+    const float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678f) sink[0] = s;
+}
+
 template <bool S, bool C, bool D>
 const void *kptr() { return reinterpret_cast<const void *>(&trace_kernel<S, C, D>); }
 
@@ -644,6 +672,15 @@ cudaError_t launch_trace(const KParams &p, KernelChoice c, unsigned blocks, size
     const void *fn = kernel_ptr(c);
     void *args[] = {const_cast<KParams *>(&p)};
     return cudaLaunchKernel(fn, dim3(blocks), dim3(kBlockThreads), args, smem_bytes, stream);
+}
+
+cudaError_t launch_mb_gather(const void *table, uint32_t n_records, uint32_t iters, unsigned blocks, float *sink, cudaStream_t stream) {
+    mb_gather_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4 *>(table), n_records, iters, sink);
+    return cudaGetLastError();
+}
+cudaError_t launch_mb_ffma(uint32_t iters, unsigned blocks, float *sink, cudaStream_t stream) {
+    mb_ffma_kernel<<<blocks, 256, 0, stream>>>(iters, sink);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_scatter_all(const float *gathered, float *image, const mm_chunk *chunks, uint32_t world, uint32_t max_count,

@@ -85,6 +85,8 @@ constexpr int kBlockThreads = MM_BLOCK_THREADS;   // 32 warps/SM at <= 64 regist
 struct KernelChoice { bool smem_nodes, counters, debug; int mux; };   // mux: 0 = one ray per lane, 2 / 3 = trace_kernel_mux<K>
 const void *kernel_ptr(KernelChoice c);
 cudaError_t launch_trace(const KParams &p, KernelChoice c, unsigned blocks, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_mb_gather(const void *table, uint32_t n_records, uint32_t iters, unsigned blocks, float *sink, cudaStream_t stream);
+cudaError_t launch_mb_ffma(uint32_t iters, unsigned blocks, float *sink, cudaStream_t stream);
 cudaError_t launch_scatter_all(const float *gathered, float *image, const mm_chunk *chunks, uint32_t world, uint32_t max_count,
                                uint32_t n_groups, uint32_t chunk, uint32_t W, uint32_t H, cudaStream_t stream);
 cudaError_t launch_blur(const float *src, float *dst, uint32_t W, uint32_t H, cudaStream_t stream);

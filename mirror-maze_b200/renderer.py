@@ -150,6 +150,12 @@ class Renderer:
     def present_blur_device(self, src_ptr, dst_ptr, width, height):
         self._ck(self._lib.mm_present_blur_device(self._ctx, src_ptr, dst_ptr, width, height))
 
+    def microbench(self, kind, table_bytes=0):
+        """kind 0: GB/s of the traversal's per-visit fetch pattern from a table of table_bytes; kind 1: T FP32 FMA lane-instr/s."""
+        out = C.c_double()
+        self._ck(self._lib.mm_microbench(self._ctx, kind, table_bytes, C.byref(out)))
+        return float(out.value)
+
     def selftest_quotient(self, n_pairs, seed=1):
         """Mismatches between the shared-reciprocal slab quotient and __fdiv_rn over n_pairs samples (must be 0)."""
         bad = C.c_uint64()
