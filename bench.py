@@ -325,7 +325,8 @@ def run_ours(a):
                 "node_fetch": {"achieved": round(node_gbs, 1), "peak": round(gather_peak, 1), "unit": "GB/s", "frac": round(node_gbs / gather_peak, 4) if gather_peak else None,
                                "def": "algorithmic node+primitive bytes (64 B per inner visit + 52 B per rect test) over the kernel time, against the "
                                       "measured rate of the same fetch pattern (3 x 16 B + 8 B from random 128-B records) on a table of the scene's size "
-                                      f"({pair_table_bytes} B, mm_microbench)"},
+                                      f"({pair_table_bytes} B, mm_microbench); lanes of a warp share records near the root of the tree, so the traversal "
+                                      "can exceed this no-sharing rate: node fetch is not the limiter (ncu: L1 request rate 65 %)"},
                 "fp32_issue": {"achieved": round(achieved_tops, 3), "peak": round(issue_peak_max, 2), "peak_at_load_clock": round(issue_peak_now, 2),
                                "peak_measured_ffma": round(ffma_peak, 2),
                                "unit": "T lane-op/s", "frac": round(achieved_tops / issue_peak_max, 4),
