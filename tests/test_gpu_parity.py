@@ -358,3 +358,10 @@ def test_rcp_slab_variant_matches_oracle(mm, oracle, noise, scenes, renderer, na
     assert_same(renderer.render(u, p, ch, debug=True), ref)
     p.flags = mm.FLAG_RCP_SLAB | mm.FLAG_FORCE_LITERAL          # general min/max form for every ray
     assert_same(renderer.render(u, p, ch, debug=True), ref)
+
+
+def test_roofline_microbenchmarks(renderer):
+    """mm_microbench: measured peaks for the node-fetch and FP32-issue rooflines (plausibility only)."""
+    assert 500.0 < renderer.microbench(0, 94 * 1024) < 40000.0         # GB/s of useful bytes, L1-resident table
+    assert 500.0 < renderer.microbench(0, 6 * 1024 * 1024) < 40000.0   # L2-resident table
+    assert 10.0 < renderer.microbench(1) < 40.0                        # T lane-instr/s (148 SMs x 128 lanes x <= 1.965 GHz = 37.2)
