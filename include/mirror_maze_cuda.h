@@ -78,14 +78,10 @@ typedef struct mm_params {
 
 #define MM_FLAG_COUNTERS      1u   /* fill mm_counters beyond `rays` (slower kernel variant)          */
 #define MM_FLAG_FORCE_LITERAL 2u   /* use the literal-divide traversal for every ray (validation)     */
-#define MM_FLAG_FORCE_GLOBAL  4u   /* read BVH child pairs through L1 from global memory (the default) */
-#define MM_FLAG_MUX2         16u   /* experimental: two rays per lane, ray state in shared memory      */
-#define MM_FLAG_MUX3         32u   /* experimental: three rays per lane                                 */
 #define MM_FLAG_RCP_SLAB     64u   /* opt-in arithmetic variant: slab quotients (b - o) * RN(1/d) instead of the literal
                                       (b - o) / d of shaders.metal:88-93 — what a fast-math compile of the shader amounts to.
                                       NOT the default; the oracle implements the same rule under the same flag and the
                                       kernel matches it bit for bit, but results differ from the literal mode's.       */
-#define MM_FLAG_FORCE_SHARED  8u   /* stage BVH child pairs in shared memory when they fit twice per SM */
 
 /* Exact event counts of one render call; identical on CPU oracle and GPU (SURVEY §8 d). */
 typedef struct mm_counters {
@@ -192,7 +188,7 @@ int mm_stream(mm_ctx *ctx, void **stream);
 /* Static facts of the loaded scene / selected kernel (for reports). */
 typedef struct mm_scene_info {
     uint32_t n_planes, n_nodes, bvh_depth, max_leaf;
-    uint32_t nodes_in_shared;   /* 1 when the traversal reads child pairs from shared memory          */
+    uint32_t nodes_in_shared;   /* always 0: child pairs are read through L1 (kept for layout stability) */
     uint32_t fast_slab_ok;      /* 1 when scene bounds allow the shared-reciprocal exact slab test    */
     uint32_t smem_bytes, block_threads, blocks_per_sm, n_sms;
 } mm_scene_info;

@@ -12,10 +12,6 @@ _LIB_NAME = "libmirror_maze_cuda.so"
 MAX_STACK = 48
 FLAG_COUNTERS = 1
 FLAG_FORCE_LITERAL = 2
-FLAG_FORCE_GLOBAL = 4
-FLAG_FORCE_SHARED = 8
-FLAG_MUX2 = 16
-FLAG_MUX3 = 32
 FLAG_RCP_SLAB = 64
 
 ERR_NAMES = {0: "MM_OK", -1: "MM_ERR_INVALID", -2: "MM_ERR_CUDA", -3: "MM_ERR_NO_SCENE", -4: "MM_ERR_BVH",

@@ -43,7 +43,6 @@ struct mm_ctx {
     uint32_t last_smem = 0, last_blocks_per_sm = 0;
     const void *cfg_fn = nullptr;     // kernel variant whose attributes / occupancy were last set up
     size_t cfg_smem = 0;
-    bool last_smem_nodes = false;
 };
 
 static std::string g_create_err;
@@ -60,15 +59,6 @@ static std::string g_create_err;
 static int fail(mm_ctx *ctx, int code, const std::string &msg) {
     ctx->err = msg;
     return code;
-}
-
-static size_t smem_nodes_limit(bool forced) {
-    // Child pairs are read through L1 (ld.global.nc, one 128-B line per pair) by default: measured on B200 it beats a
-    // per-block shared-memory copy (48.9 vs 50.5 ms on the 32x32-maze frame, profiles/r1_sched_sweep.txt).  The
-    // shared-memory variant is kept behind MM_FLAG_FORCE_SHARED / MM_SMEM_NODE_LIMIT (bytes) for trees that fit twice per SM.
-    const char *e = getenv("MM_SMEM_NODE_LIMIT");
-    if (e) return (size_t)strtoull(e, nullptr, 10);
-    return forced ? 105 * 1024 : 0;
 }
 
 extern "C" {
@@ -239,22 +229,10 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
     p.chunks = ctx->d_chunks; p.noise = ctx->d_noise;
     p.counters = ctx->d_counters;
 
-    const size_t red_bytes = 3 * kBlockThreads * sizeof(float);
-    const size_t pair_bytes = (size_t)ctx->n_pairs * kPairSmemBytes;
-    bool smem_nodes = ctx->n_pairs > 0 && !(par->flags & MM_FLAG_FORCE_GLOBAL) && pair_bytes <= smem_nodes_limit((par->flags & MM_FLAG_FORCE_SHARED) != 0) &&
-                      red_bytes + pair_bytes <= ctx->smem_optin;
-    int mux = (par->flags & MM_FLAG_MUX3) ? 3 : ((par->flags & MM_FLAG_MUX2) ? 2 : 0);
-    if (const char *e = getenv("MM_MUX")) mux = atoi(e);                 // developer override
-    if (mux != 2 && mux != 3) mux = 0;
-    if (ctx->max_leaf > 30 || ctx->n_pairs == 0 || (par->flags & MM_FLAG_RCP_SLAB)) mux = 0;                // descriptor bit budget of the K-rays-per-lane kernel
-    if (mux) smem_nodes = false;
-    L.choice.smem_nodes = smem_nodes;
-    L.choice.mux = mux;
     L.choice.debug = debug;
     L.choice.counters = debug || (par->flags & MM_FLAG_COUNTERS);
-    const uint64_t paths_per_block = (uint64_t)kBlockThreads * (mux ? mux : 1);
-    L.smem = mux ? (size_t)6 * 16 * mux * kBlockThreads : red_bytes + (smem_nodes ? pair_bytes : 0);
-    const uint64_t blocks = (p.total_paths + paths_per_block - 1) / paths_per_block;
+    L.smem = 3 * kBlockThreads * sizeof(float);                          // reduction scratch
+    const uint64_t blocks = (p.total_paths + kBlockThreads - 1) / kBlockThreads;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, MM_ERR_UNSUPPORTED, "too many paths for one launch");
     L.blocks = (unsigned)blocks;
     return MM_OK;
@@ -270,7 +248,6 @@ int do_launch(mm_ctx *ctx, Launch &L) {
         ctx->cfg_fn = fn; ctx->cfg_smem = L.smem;
     }
     ctx->last_smem = (uint32_t)L.smem;
-    ctx->last_smem_nodes = L.choice.smem_nodes;
     CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(launch_trace(L.p, L.choice, L.blocks, L.smem, ctx->stream));
@@ -504,7 +481,7 @@ int mm_get_scene_info(mm_ctx *ctx, mm_scene_info *out) {
     if (!ctx || !out) return MM_ERR_INVALID;
     if (!ctx->have_scene) return fail(ctx, MM_ERR_NO_SCENE, "no scene uploaded");
     out->n_planes = ctx->n_slots; out->n_nodes = ctx->n_nodes; out->bvh_depth = ctx->depth; out->max_leaf = ctx->max_leaf;
-    out->nodes_in_shared = ctx->last_smem_nodes ? 1u : 0u;
+    out->nodes_in_shared = 0u;   // child pairs are read through L1 (a shared-memory copy measured slower, profiles/r1_sched_sweep.txt)
     out->fast_slab_ok = ctx->fast_ok ? 1u : 0u;
     out->smem_bytes = ctx->last_smem; out->block_threads = kBlockThreads; out->blocks_per_sm = ctx->last_blocks_per_sm;
     out->n_sms = (uint32_t)ctx->n_sms;

@@ -105,85 +105,50 @@ __device__ __forceinline__ bool rcp_safe(float o, float d) {
 
 struct Tally { uint32_t inner, leaf, rect, max_stack; };
 
-// Where a lane's child pairs come from.
-//  SMEM:   SoA arrays in shared memory (bank group = pair index mod 8, so lanes on different pairs spread over all
-//          banks) in two orderings per axis: (c0.min, c0.max, c1.min, c1.max) for rays travelling up the axis and
-//          (c0.max, c0.min, c1.max, c1.min) for rays travelling down, so that component .x/.z is always the near plane.
-//  global: the 128-B PairRec (both orderings, one L1 line per pair) through ld.global.nc.
-template <bool SMEM>
-struct PairView {
-    const float4 *x, *y, *z;      // SMEM: base of the "up" arrays; the "down" arrays follow at +n_pairs
-    const uint2 *l;
-    const PairRec *g;
-    uint32_t n_pairs;
-};
-
-// Per-ray view: the three per-axis base pointers already include the travel-order choice, so that a visit's address
-// arithmetic is one multiply-add per load.
-template <bool SMEM>
-struct RayPairs {
-    const char *bx, *by, *bz, *bl;
-    // nx/ny/nz: 1 when the ray travels down that axis (fast path only; the literal path always passes 0)
-    __device__ __forceinline__ RayPairs(const PairView<SMEM> &pv, uint32_t nx, uint32_t ny, uint32_t nz) {
-        if (SMEM) {
-            bx = reinterpret_cast<const char *>(pv.x + nx * pv.n_pairs);
-            by = reinterpret_cast<const char *>(pv.y + ny * pv.n_pairs);
-            bz = reinterpret_cast<const char *>(pv.z + nz * pv.n_pairs);
-            bl = reinterpret_cast<const char *>(pv.l);
-        } else {
-            const char *b = reinterpret_cast<const char *>(pv.g);
-            bx = b + 64 * nx; by = b + 16 + 64 * ny; bz = b + 32 + 64 * nz; bl = b + 48;
-            // keep the three pointers live: ptxas otherwise re-derives them from sign(dir) at every node (5 instructions each)
-            asm("" : "+l"(bx)); asm("" : "+l"(by)); asm("" : "+l"(bz));
-        }
-    }
-    __device__ __forceinline__ void load(uint32_t p, float4 &vx, float4 &vy, float4 &vz, uint2 &lk) const {
-        if (SMEM) {
-            vx = *reinterpret_cast<const float4 *>(bx + 16u * p); vy = *reinterpret_cast<const float4 *>(by + 16u * p);
-            vz = *reinterpret_cast<const float4 *>(bz + 16u * p); lk = *reinterpret_cast<const uint2 *>(bl + 8u * p);
-        } else {
-            const size_t off = (size_t)p * sizeof(PairRec);
-            vx = __ldg(reinterpret_cast<const float4 *>(bx + off)); vy = __ldg(reinterpret_cast<const float4 *>(by + off));
-            vz = __ldg(reinterpret_cast<const float4 *>(bz + off)); lk = __ldg(reinterpret_cast<const uint2 *>(bl + off));
-        }
-    }
-};
-
 constexpr uint32_t CUR_END = 0xFFFFFFFFu;   // traversal finished
 
-// One interior visit of intersect_bvh_iterative (shaders.metal:134-154): slab-test both children (:87-95), order them,
-// descend / pop.
-//
-// FAST (guarded ranges, no zero / NaN / inf anywhere): the quotients are the exact RN((b - o)/d) of the literal code and
-// (b_min - o)/d <= (b_max - o)/d holds for d > 0 by monotonicity of rounding (reversed for d < 0), so with the pair
-// loaded in travel order min(t1,t2) is the first and max(t1,t2) the second component: tmin = max3(near), tmax = min3(far).
-// The literal `dist` values are never materialised: with hit_k = (tmax_k >= tmin_k && tmin_k < t && tmax_k > 0) and
-// dist_k = hit_k ? tmin_k : 1e30 (tmin_k < t <= 1e30 when hit), `dist1 > dist2` is hit2 && (!hit1 || tmin1 > tmin2),
+// ---- packed FP32 (Blackwell FADD2 / FMUL2 / FFMA2: two IEEE-RN fp32 operations per issued instruction) ------------------
+// The kernel is bound by instruction issue, not by the FMA pipe (ncu: issue slots 85 % busy, FMA pipe 43 %), and the
+// twelve slab quotients of a visit are six pairs of identical, independent operation chains — so they are issued as
+// add.rn.f32x2 / mul.rn.f32x2 / fma.rn.f32x2 on register pairs: per lane the results are the bits of the scalar
+// instructions, at half the issue slots.
+typedef unsigned long long f2;   // two fp32 in a 64-bit register pair (low word = first component)
+__device__ __forceinline__ f2 pack2(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2f(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); (void)b; return a; }
+__device__ __forceinline__ float hi2f(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); (void)a; return b; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+// Per-ray constants of the packed slab test: x and y share register pairs, z is duplicated.
+struct RayK {
+    f2 no_xy, nd_xy, r_xy, rl_xy;   // (-o.x, -o.y), (-d.x, -d.y), (r.x, r.y), (rl.x, rl.y)
+    f2 no_zz, nd_zz, r_zz, rl_zz;
+};
+
+// Two slab quotients at once: x = b - o, then either the exact shared-reciprocal sequence (== RN(x/d), see the file header
+// and docs/exact_quotient.md) or, in the opt-in MM_FLAG_RCP_SLAB arithmetic, x * RN(1/d).
+template <bool RCP>
+__device__ __forceinline__ f2 quot2(f2 b, f2 no, f2 nd, f2 r, f2 rl) {
+    const f2 x = add2(b, no);                  // b + (-o) == b - o
+    if (RCP) return mul2(x, r);
+    const f2 p = mul2(x, rl);
+    const f2 q1 = fma2(x, r, p);
+    const f2 e = fma2(nd, q1, x);              // x - d*q1, exact
+    return fma2(e, r, q1);
+}
+
+// The decisions of one interior visit (shaders.metal:140-154) from the children's [lo, hi] slab intervals.
+// The literal `dist` values are never materialised: with hit_k = (hi_k >= lo_k && lo_k < t && hi_k > 0) and
+// dist_k = hit_k ? lo_k : 1e30 (lo_k < t <= 1e30 when hit), `dist1 > dist2` is hit2 && (!hit1 || lo1 > lo2),
 // `dist_near == 1e30` is !hit1 && !hit2 and `dist_far != 1e30` is hit1 && hit2 — the same decisions, fewer instructions.
-template <bool FAST, bool CNT, bool RCP = false>
-__device__ __forceinline__ void inner_step(const float4 &bx, const float4 &by, const float4 &bz, const uint2 &lk, const Axis &ax,
-                                           const Axis &ay, const Axis &az, float t, uint32_t &cur, uint32_t &head, uint32_t *stack,
-                                           Tally &tl) {
-    float lo1, hi1, lo2, hi2;
-    if (FAST) {
-        lo1 = fmaxf(fmaxf(quot<true, RCP>(bx.x, ax), quot<true, RCP>(by.x, ay)), quot<true, RCP>(bz.x, az));
-        hi1 = fminf(fminf(quot<true, RCP>(bx.y, ax), quot<true, RCP>(by.y, ay)), quot<true, RCP>(bz.y, az));
-        lo2 = fmaxf(fmaxf(quot<true, RCP>(bx.z, ax), quot<true, RCP>(by.z, ay)), quot<true, RCP>(bz.z, az));
-        hi2 = fminf(fminf(quot<true, RCP>(bx.w, ax), quot<true, RCP>(by.w, ay)), quot<true, RCP>(bz.w, az));
-    } else {
-        float t1 = quot<false, RCP>(bx.x, ax), t2 = quot<false, RCP>(bx.y, ax);
-        lo1 = fminf(t1, t2); hi1 = fmaxf(t1, t2);
-        t1 = quot<false, RCP>(by.x, ay); t2 = quot<false, RCP>(by.y, ay);
-        lo1 = fmaxf(lo1, fminf(t1, t2)); hi1 = fminf(hi1, fmaxf(t1, t2));
-        t1 = quot<false, RCP>(bz.x, az); t2 = quot<false, RCP>(bz.y, az);
-        lo1 = fmaxf(lo1, fminf(t1, t2)); hi1 = fminf(hi1, fmaxf(t1, t2));
-        t1 = quot<false, RCP>(bx.z, ax); t2 = quot<false, RCP>(bx.w, ax);
-        lo2 = fminf(t1, t2); hi2 = fmaxf(t1, t2);
-        t1 = quot<false, RCP>(by.z, ay); t2 = quot<false, RCP>(by.w, ay);
-        lo2 = fmaxf(lo2, fminf(t1, t2)); hi2 = fminf(hi2, fmaxf(t1, t2));
-        t1 = quot<false, RCP>(bz.z, az); t2 = quot<false, RCP>(bz.w, az);
-        lo2 = fmaxf(lo2, fminf(t1, t2)); hi2 = fminf(hi2, fmaxf(t1, t2));
-    }
+template <bool CNT>
+__device__ __forceinline__ void descend(float lo1, float hi1, float lo2, float hi2, const uint2 &lk, float t, uint32_t &cur, uint32_t &head,
+                                        uint32_t *stack, Tally &tl) {
     const bool hit1 = (hi1 >= lo1) & (lo1 < t) & (hi1 > 0.0f);          // :94
     const bool hit2 = (hi2 >= lo2) & (lo2 < t) & (hi2 > 0.0f);
     const bool swap = hit2 & (!hit1 | (lo1 > lo2));                     // :140, ties keep the left child first
@@ -197,6 +162,46 @@ __device__ __forceinline__ void inner_step(const float4 &bx, const float4 &by, c
             if (CNT) tl.max_stack = max(tl.max_stack, head);
         }
     }
+}
+
+// One interior visit, fast form (guarded operand ranges: no zero / NaN / inf anywhere).  The quotients are the exact
+// RN((b - o)/d) of the literal code; the record is loaded with x and z in the ray's travel order, so their near plane is
+// the first and their far plane the second value (rounding is monotone), y keeps the literal min/max:
+//   A = (c0.near.x, c0.min.y | c0.far.x, c0.max.y)   B likewise for child 1   Z = (c0.near.z, c1.near.z | c0.far.z, c1.far.z)
+template <bool CNT, bool RCP>
+__device__ __forceinline__ void inner_step_packed(const ulonglong2 &A, const ulonglong2 &B, const ulonglong2 &Z, const uint2 &lk,
+                                                  const RayK &k, float t, uint32_t &cur, uint32_t &head, uint32_t *stack, Tally &tl) {
+    const f2 an = quot2<RCP>(A.x, k.no_xy, k.nd_xy, k.r_xy, k.rl_xy), af = quot2<RCP>(A.y, k.no_xy, k.nd_xy, k.r_xy, k.rl_xy);
+    const f2 bn = quot2<RCP>(B.x, k.no_xy, k.nd_xy, k.r_xy, k.rl_xy), bf = quot2<RCP>(B.y, k.no_xy, k.nd_xy, k.r_xy, k.rl_xy);
+    const f2 zn = quot2<RCP>(Z.x, k.no_zz, k.nd_zz, k.r_zz, k.rl_zz), zf = quot2<RCP>(Z.y, k.no_zz, k.nd_zz, k.r_zz, k.rl_zz);
+    const float a1 = hi2f(an), a2 = hi2f(af), b1 = hi2f(bn), b2 = hi2f(bf);
+    const float lo1 = fmaxf(fmaxf(lo2f(an), fminf(a1, a2)), lo2f(zn));
+    const float hi1 = fminf(fminf(lo2f(af), fmaxf(a1, a2)), lo2f(zf));
+    const float lo2 = fmaxf(fmaxf(lo2f(bn), fminf(b1, b2)), hi2f(zn));
+    const float hi2 = fminf(fminf(lo2f(bf), fmaxf(b1, b2)), hi2f(zf));
+    descend<CNT>(lo1, hi1, lo2, hi2, lk, t, cur, head, stack, tl);
+}
+
+// One interior visit, general form: the literal min/max of shaders.metal:88-93 with NaN-dropping fmin/fmax, for rays whose
+// operands are outside the guarded ranges (zero / subnormal / huge / NaN components) or under MM_FLAG_FORCE_LITERAL.
+// Reads the record in its "up" order: a = (c0.min.x, c0.min.y, c0.max.x, c0.max.y), zu = (c0.min.z, c1.min.z, c0.max.z, c1.max.z).
+template <bool CNT, bool RCP>
+__device__ __forceinline__ void inner_step_general(const float4 &a, const float4 &b, const float4 &zu, const uint2 &lk, const Axis &ax,
+                                                   const Axis &ay, const Axis &az, float t, uint32_t &cur, uint32_t &head,
+                                                   uint32_t *stack, Tally &tl) {
+    float t1 = quot<false, RCP>(a.x, ax), t2 = quot<false, RCP>(a.z, ax);
+    float lo1 = fminf(t1, t2), hi1 = fmaxf(t1, t2);
+    t1 = quot<false, RCP>(a.y, ay); t2 = quot<false, RCP>(a.w, ay);
+    lo1 = fmaxf(lo1, fminf(t1, t2)); hi1 = fminf(hi1, fmaxf(t1, t2));
+    t1 = quot<false, RCP>(zu.x, az); t2 = quot<false, RCP>(zu.z, az);
+    lo1 = fmaxf(lo1, fminf(t1, t2)); hi1 = fminf(hi1, fmaxf(t1, t2));
+    t1 = quot<false, RCP>(b.x, ax); t2 = quot<false, RCP>(b.z, ax);
+    float lo2 = fminf(t1, t2), hi2 = fmaxf(t1, t2);
+    t1 = quot<false, RCP>(b.y, ay); t2 = quot<false, RCP>(b.w, ay);
+    lo2 = fmaxf(lo2, fminf(t1, t2)); hi2 = fminf(hi2, fmaxf(t1, t2));
+    t1 = quot<false, RCP>(zu.y, az); t2 = quot<false, RCP>(zu.w, az);
+    lo2 = fmaxf(lo2, fminf(t1, t2)); hi2 = fminf(hi2, fmaxf(t1, t2));
+    descend<CNT>(lo1, hi1, lo2, hi2, lk, t, cur, head, stack, tl);
 }
 
 // One leaf visit (shaders.metal:127-129 with ray_rect_intersect :51-67 inlined), then pop / finish.
@@ -226,12 +231,12 @@ __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 or
 }
 
 // intersect_bvh_iterative (shaders.metal:115-156) for the rays of one warp.  Every lane of the warp calls this together
-// (lanes without a ray pass alive = false) and the warp votes, every step, on which body to execute: the interior body
-// runs while the lanes standing at an interior node outweigh the lanes waiting at a leaf (nI >= kLeafWeight * nL),
-// otherwise the waiting lanes test their rects.  Each lane still performs exactly the reference's sequence of visits
-// for its own ray; only the interleaving between lanes changes.  (A plain while-while loop — all lanes descend to a
-// leaf, then all test — left 12 of 32 lanes active in the interior body; see profiles/.)
-// `lit` lanes (operands outside the guarded ranges, or MM_FLAG_FORCE_LITERAL) use the literal-divide slab test.
+// (lanes without a ray pass alive = false) and the warp votes on which body to execute: the interior body runs (kInnerReps
+// visits per vote) while the lanes standing at an interior node outweigh the lanes waiting at a leaf
+// (nI >= kLeafWeight * nL), otherwise the waiting lanes test their rects.  Each lane still performs exactly the
+// reference's sequence of visits for its own ray; only the interleaving between lanes changes.  (A plain while-while
+// loop — all lanes descend to a leaf, then all test — left 12 of 32 lanes active in the interior body; see profiles/.)
+// `lit` lanes (operands outside the guarded ranges, or MM_FLAG_FORCE_LITERAL) use the general slab form.
 #ifndef MM_LEAF_WEIGHT
 #define MM_LEAF_WEIGHT 4
 #endif
@@ -241,31 +246,26 @@ constexpr uint32_t kLeafWeight = MM_LEAF_WEIGHT;   // measured best on B200 (pro
 #endif
 constexpr uint32_t kInnerReps = MM_INNER_REPS;
 
-// MIXED = false: no lane of the warp is literal (the common case; the loop then contains no literal-divide code).
+// MIXED = false: no lane of the warp is literal (the common case; the loop then contains no general-form code).
 // Not inlined on purpose: the call boundary parks the path state that the traversal does not touch (throughput,
 // radiance, RNG state, counters, pixel bookkeeping) in the caller's frame, so the traversal loop has the whole 64-register
-// budget and keeps its per-ray constants (reciprocal corrections, travel-order offsets, table base) live instead of
-// rematerialising them at every node.
+// budget for its per-ray constants.
 struct Hit { float t; uint32_t slot; };
-#ifndef MM_TRAVERSE_INLINE
-#define MM_TRAVERSE_ATTR __noinline__
-#else
-#define MM_TRAVERSE_ATTR __forceinline__
-#endif
-template <bool MIXED, bool SMEM, bool CNT, bool RCP = false>
-__device__ MM_TRAVERSE_ATTR Hit traverse(PairView<SMEM> pv, const RectI *__restrict__ rects, uint32_t root, bool alive, bool lit,
-                                         V3 ori, V3 dir, float beam_t, uint32_t beam_slot, uint32_t *stack, Tally *tlp) {
+template <bool MIXED, bool CNT, bool RCP>
+__device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const RectI *__restrict__ rects, uint32_t root, bool alive,
+                                     bool lit, V3 ori, V3 dir, float beam_t, uint32_t beam_slot, uint32_t *stack, Tally *tlp) {
     Tally tl = {0u, 0u, 0u, 0u};
-    Axis ax, ay, az;
-    ax.o = ori.x; ax.d = dir.x; ay.o = ori.y; ay.d = dir.y; az.o = ori.z; az.d = dir.z;
-    ax.r = __frcp_rn(ax.d); ax.rl = fmul(__fmaf_rn(-ax.d, ax.r, 1.0f), ax.r);
-    ay.r = __frcp_rn(ay.d); ay.rl = fmul(__fmaf_rn(-ay.d, ay.r, 1.0f), ay.r);
-    az.r = __frcp_rn(az.d); az.rl = fmul(__fmaf_rn(-az.d, az.r, 1.0f), az.r);
-#ifdef MM_PIN_RL
-    asm("" : "+f"(ax.rl)); asm("" : "+f"(ay.rl)); asm("" : "+f"(az.rl));   // keep the reciprocal corrections live (no per-node rematerialisation)
-#endif
-    const uint32_t nx = (!lit && ax.d < 0.0f) ? 1u : 0u, ny = (!lit && ay.d < 0.0f) ? 1u : 0u, nz = (!lit && az.d < 0.0f) ? 1u : 0u;
-    const RayPairs<SMEM> rp(pv, nx, ny, nz);
+    const float rx = __frcp_rn(dir.x), ry = __frcp_rn(dir.y), rz = __frcp_rn(dir.z);
+    const float rlx = fmul(__fmaf_rn(-dir.x, rx, 1.0f), rx), rly = fmul(__fmaf_rn(-dir.y, ry, 1.0f), ry),
+                rlz = fmul(__fmaf_rn(-dir.z, rz, 1.0f), rz);
+    RayK k;
+    k.no_xy = pack2(-ori.x, -ori.y); k.nd_xy = pack2(-dir.x, -dir.y); k.r_xy = pack2(rx, ry); k.rl_xy = pack2(rlx, rly);
+    k.no_zz = pack2(-ori.z, -ori.z); k.nd_zz = pack2(-dir.z, -dir.z); k.r_zz = pack2(rz, rz); k.rl_zz = pack2(rlz, rlz);
+    // per-ray record pointers with the travel order folded in: A|B at +0 (x up) / +32 (x down), Z at +64 (z up) / +80 (z down)
+    const char *base = reinterpret_cast<const char *>(pairs);
+    const char *pAB = base + ((!lit && dir.x < 0.0f) ? 32 : 0);
+    const char *pZ = base + 64 + ((!lit && dir.z < 0.0f) ? 16 : 0);
+    asm("" : "+l"(pAB)); asm("" : "+l"(pZ));      // keep them live: ptxas otherwise re-derives them from sign(dir) at every node
     uint32_t cur = alive ? root : CUR_END, head = 0, slot = beam_slot;
     float t = beam_t;
     while (true) {
@@ -274,16 +274,26 @@ __device__ MM_TRAVERSE_ATTR Hit traverse(PairView<SMEM> pv, const RectI *__restr
         const unsigned mI = __ballot_sync(0xFFFFFFFFu, isI), mL = __ballot_sync(0xFFFFFFFFu, isL);
         if ((mI | mL) == 0u) break;
         if (mI != 0u && __popc(mI) >= kLeafWeight * __popc(mL)) {
-            // kInnerReps interior visits per vote: the vote and loop control cost ~18 instructions against ~100 for a visit
 #pragma unroll 1
             for (uint32_t rep = 0; rep < kInnerReps; rep++) {
                 if ((cur >> 24) == 0u) {
-                    float4 bx, by, bz;
-                    uint2 lk;
-                    rp.load(cur, bx, by, bz, lk);
+                    const size_t off = (size_t)cur * sizeof(PairRec);
+                    const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(base + 96 + off));
                     if (CNT) tl.inner++;
-                    if (!MIXED || !lit) inner_step<true, CNT, RCP>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
-                    else inner_step<false, CNT, RCP>(bx, by, bz, lk, ax, ay, az, t, cur, head, stack, tl);
+                    if (!MIXED || !lit) {
+                        const ulonglong2 A = __ldg(reinterpret_cast<const ulonglong2 *>(pAB + off));
+                        const ulonglong2 B = __ldg(reinterpret_cast<const ulonglong2 *>(pAB + off + 16));
+                        const ulonglong2 Z = __ldg(reinterpret_cast<const ulonglong2 *>(pZ + off));
+                        inner_step_packed<CNT, RCP>(A, B, Z, lk, k, t, cur, head, stack, tl);
+                    } else {
+                        const float4 a = __ldg(reinterpret_cast<const float4 *>(base + off)), b = __ldg(reinterpret_cast<const float4 *>(base + off + 16));
+                        const float4 zu = __ldg(reinterpret_cast<const float4 *>(base + off + 64));
+                        Axis ax, ay, az;
+                        ax.o = ori.x; ax.d = dir.x; ax.r = rx; ax.rl = rlx;
+                        ay.o = ori.y; ay.d = dir.y; ay.r = ry; ay.rl = rly;
+                        az.o = ori.z; az.d = dir.z; az.r = rz; az.rl = rlz;
+                        inner_step_general<CNT, RCP>(a, b, zu, lk, ax, ay, az, t, cur, head, stack, tl);
+                    }
                 }
             }
         } else {
@@ -311,35 +321,11 @@ __device__ __forceinline__ void sample_noise_xy(const uint8_t *noise, uint32_t n
     ny = fdiv((float)c.y, 255.0f);
 }
 
-template <bool SMEM_NODES, bool CNT, bool DBG>
+template <bool CNT, bool DBG>
 __global__ void __launch_bounds__(kBlockThreads, MM_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *red = reinterpret_cast<float *>(smem_raw);                      // 3 * kBlockThreads floats
-    PairView<SMEM_NODES> pv;
-    pv.g = P.pairs;
-    pv.n_pairs = P.n_pairs;
-    if (SMEM_NODES) {
-        // smem: [x up | x down | y up | y down | z up | z down] float4[n_pairs] each, then links uint2[n_pairs]
-        float4 *sx = reinterpret_cast<float4 *>(smem_raw + 3 * kBlockThreads * sizeof(float));
-        float4 *sy = sx + 2 * P.n_pairs, *sz = sy + 2 * P.n_pairs;
-        uint2 *sl = reinterpret_cast<uint2 *>(sz + 2 * P.n_pairs);
-        const float4 *src = reinterpret_cast<const float4 *>(P.pairs);
-        for (uint32_t i = threadIdx.x; i < P.n_pairs * 8u; i += kBlockThreads) {
-            const uint32_t pr = i >> 3, c = i & 7u;
-            if (c == 7u) continue;
-            const float4 v = src[i];
-            if (c == 0) sx[pr] = v;
-            else if (c == 1) sy[pr] = v;
-            else if (c == 2) sz[pr] = v;
-            else if (c == 3) sl[pr] = make_uint2(__float_as_uint(v.x), __float_as_uint(v.y));
-            else if (c == 4) sx[pr + P.n_pairs] = v;
-            else if (c == 5) sy[pr + P.n_pairs] = v;
-            else sz[pr + P.n_pairs] = v;
-        }
-        pv.x = sx; pv.y = sy; pv.z = sz; pv.l = sl;
-        __syncthreads();
-    }
 
     const uint64_t path = (uint64_t)blockIdx.x * kBlockThreads + threadIdx.x;
     const bool active = path < P.total_paths;
@@ -410,11 +396,11 @@ trace_kernel(const __grid_constant__ KParams P) {
             const bool any_lit = __any_sync(0xFFFFFFFFu, alive && lit);
             Hit h;
             if (P.rcp_mode) {
-                if (!any_lit) h = traverse<false, SMEM_NODES, CNT, true>(pv, P.rects, root, alive, false, ori, dir, t, slot, stack, &tl);
-                else h = traverse<true, SMEM_NODES, CNT, true>(pv, P.rects, root, alive, lit, ori, dir, t, slot, stack, &tl);
+                if (!any_lit) h = traverse<false, CNT, true>(P.pairs, P.rects, root, alive, false, ori, dir, t, slot, stack, &tl);
+                else h = traverse<true, CNT, true>(P.pairs, P.rects, root, alive, lit, ori, dir, t, slot, stack, &tl);
             } else {
-                if (!any_lit) h = traverse<false, SMEM_NODES, CNT>(pv, P.rects, root, alive, false, ori, dir, t, slot, stack, &tl);
-                else h = traverse<true, SMEM_NODES, CNT>(pv, P.rects, root, alive, lit, ori, dir, t, slot, stack, &tl);
+                if (!any_lit) h = traverse<false, CNT, false>(P.pairs, P.rects, root, alive, false, ori, dir, t, slot, stack, &tl);
+                else h = traverse<true, CNT, false>(P.pairs, P.rects, root, alive, lit, ori, dir, t, slot, stack, &tl);
             }
             t = h.t; slot = h.slot;
             if (alive) {
@@ -530,8 +516,6 @@ trace_kernel(const __grid_constant__ KParams P) {
         }
     }
 }
-
-#include "trace_mux.cuh"
 
 // De-interleave gathered tiles into the frame (consumer side of the multi-GPU tile gather).
 __global__ void scatter_kernel(const float4 *__restrict__ tiles, float4 *__restrict__ image, const mm_chunk *__restrict__ chunks,
@@ -649,23 +633,14 @@ __global__ void __launch_bounds__(256) mb_ffma_kernel(uint32_t iters, float *__r
     if (s == 12345.678f) sink[0] = s;
 }
 
-template <bool S, bool C, bool D>
-const void *kptr() { return reinterpret_cast<const void *>(&trace_kernel<S, C, D>); }
+template <bool C, bool D>
+const void *kptr() { return reinterpret_cast<const void *>(&trace_kernel<C, D>); }
 
 }  // namespace
 
-template <int K, bool C, bool D>
-const void *kptr_mux() { return reinterpret_cast<const void *>(&trace_kernel_mux<K, C, D>); }
-
 const void *kernel_ptr(KernelChoice c) {
-    if (c.mux == 2) return c.debug ? kptr_mux<2, true, true>() : (c.counters ? kptr_mux<2, true, false>() : kptr_mux<2, false, false>());
-    if (c.mux == 3) return c.debug ? kptr_mux<3, true, true>() : (c.counters ? kptr_mux<3, true, false>() : kptr_mux<3, false, false>());
-    if (c.smem_nodes) {
-        if (c.debug) return kptr<true, true, true>();
-        return c.counters ? kptr<true, true, false>() : kptr<true, false, false>();
-    }
-    if (c.debug) return kptr<false, true, true>();
-    return c.counters ? kptr<false, true, false>() : kptr<false, false, false>();
+    if (c.debug) return kptr<true, true>();
+    return c.counters ? kptr<true, false>() : kptr<false, false>();
 }
 
 cudaError_t launch_trace(const KParams &p, KernelChoice c, unsigned blocks, size_t smem_bytes, cudaStream_t stream) {

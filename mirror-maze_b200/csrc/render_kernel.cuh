@@ -7,21 +7,21 @@
 namespace mmk {
 
 // One interior node's two children, 128 B = one L1/L2 line.
-// The reference node array (32 B each, children adjacent; shaders.metal:30-35,134-135) is re-laid per inner node so that
-// one traversal step is three 16-B loads (one per slab axis) plus an 8-B link load, and stored in both travel orders:
-//   up   : x = (c0.min.x, c0.max.x, c1.min.x, c1.max.x)   for rays with dir.x > 0  (near plane first)
-//   down : x = (c0.max.x, c0.min.x, c1.max.x, c1.min.x)   for rays with dir.x < 0
-//   y, z likewise;  link = (c0.desc, c1.desc, 0, 0) with desc = link | count << 24: count > 0 is a leaf whose link is the
-//   first slot in the leaf-ordered rect array, count == 0 an interior node whose link is its pair index.
-// The kernel's shared-memory copy is SoA over pairs (see PairView in render_kernel.cu).
+// The reference node array (32 B each, children adjacent; shaders.metal:30-35,134-135) is re-laid per interior node for the
+// packed-FP32 slab test: x and y of a plane sit in adjacent words (one register pair after the load), x and z come in both
+// travel orders so that the near plane is always the first value, y keeps (min, max):
+//   a_xu = (c0.min.x, c0.min.y, c0.max.x, c0.max.y)   b_xu = the same for child 1          (rays with dir.x > 0)
+//   a_xd = (c0.max.x, c0.min.y, c0.min.x, c0.max.y)   b_xd = the same for child 1          (rays with dir.x < 0)
+//   z_u  = (c0.min.z, c1.min.z, c0.max.z, c1.max.z)   z_d = (c0.max.z, c1.max.z, c0.min.z, c1.min.z)
+//   link = (c0.desc, c1.desc, 0, 0) with desc = link | count << 24: count > 0 is a leaf whose link is the first slot in the
+//   leaf-ordered rect array, count == 0 an interior node whose link is its pair index.
+// One traversal step = two adjacent 16-B loads (a, b) + one 16-B load (z) + one 8-B load (link) from one line.
 struct __align__(16) PairRec {
-    float4 x, y, z;
+    float4 a_xu, b_xu, a_xd, b_xd, z_u, z_d;
     uint4 link;
-    float4 xd, yd, zd;
     uint4 pad;
 };
 static_assert(sizeof(PairRec) == 128, "pair record is 128 B");
-constexpr uint32_t kPairSmemBytes = 6 * 16 + 8;   // bytes of shared memory per pair (six float4 + one uint2)
 
 // One rectangle in leaf order (slot s = position in the reference `indices` array), 64 B.
 // The normal and the edge lengths are per-rect constants of ray_rect_intersect (shaders.metal:52,60-61); they are
@@ -82,7 +82,7 @@ struct KParams {
 constexpr int kBlockThreads = MM_BLOCK_THREADS;   // 32 warps/SM at <= 64 registers (measured best; profiles/r1_block_shape.txt)
 
 // Returns the kernel's static properties for the occupancy query and launch.
-struct KernelChoice { bool smem_nodes, counters, debug; int mux; };   // mux: 0 = one ray per lane, 2 / 3 = trace_kernel_mux<K>
+struct KernelChoice { bool counters, debug; };
 const void *kernel_ptr(KernelChoice c);
 cudaError_t launch_trace(const KParams &p, KernelChoice c, unsigned blocks, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_mb_gather(const void *table, uint32_t n_records, uint32_t iters, unsigned blocks, float *sink, cudaStream_t stream);

@@ -53,17 +53,18 @@ int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *
         if (nodes[i].tri_count != 0) continue;
         const mm_bvh_node &a = nodes[nodes[i].left_first], &b = nodes[nodes[i].left_first + 1];
         PairRec &p = out.pairs[pair_id[i]];
-        p.x = make_float4(a.aabb_min.x, a.aabb_max.x, b.aabb_min.x, b.aabb_max.x);
-        p.y = make_float4(a.aabb_min.y, a.aabb_max.y, b.aabb_min.y, b.aabb_max.y);
-        p.z = make_float4(a.aabb_min.z, a.aabb_max.z, b.aabb_min.z, b.aabb_max.z);
-        p.xd = make_float4(p.x.y, p.x.x, p.x.w, p.x.z);
-        p.yd = make_float4(p.y.y, p.y.x, p.y.w, p.y.z);
-        p.zd = make_float4(p.z.y, p.z.x, p.z.w, p.z.z);
+        p.a_xu = make_float4(a.aabb_min.x, a.aabb_min.y, a.aabb_max.x, a.aabb_max.y);
+        p.b_xu = make_float4(b.aabb_min.x, b.aabb_min.y, b.aabb_max.x, b.aabb_max.y);
+        p.a_xd = make_float4(a.aabb_max.x, a.aabb_min.y, a.aabb_min.x, a.aabb_max.y);
+        p.b_xd = make_float4(b.aabb_max.x, b.aabb_min.y, b.aabb_min.x, b.aabb_max.y);
+        p.z_u = make_float4(a.aabb_min.z, b.aabb_min.z, a.aabb_max.z, b.aabb_max.z);
+        p.z_d = make_float4(a.aabb_max.z, b.aabb_max.z, a.aabb_min.z, b.aabb_min.z);
         p.link = make_uint4(desc(nodes[i].left_first), desc(nodes[i].left_first + 1), 0u, 0u);
-        const float *c = &p.x.x;
+        const float c[12] = {a.aabb_min.x, a.aabb_min.y, a.aabb_min.z, a.aabb_max.x, a.aabb_max.y, a.aabb_max.z,
+                             b.aabb_min.x, b.aabb_min.y, b.aabb_min.z, b.aabb_max.x, b.aabb_max.y, b.aabb_max.z};
         for (int k = 0; k < 12; k++) fast_ok = fast_ok && coord_ok(c[k]);
         // the travel-ordered fast path also needs min <= max on every axis (true for every box the builder emits)
-        fast_ok = fast_ok && p.x.x <= p.x.y && p.x.z <= p.x.w && p.y.x <= p.y.y && p.y.z <= p.y.w && p.z.x <= p.z.y && p.z.z <= p.z.w;
+        for (int k = 0; k < 3; k++) fast_ok = fast_ok && c[k] <= c[k + 3] && c[k + 6] <= c[k + 9];
     }
     out.n_pairs = n_pairs;
     out.root_link = nodes[0].tri_count > 0 ? nodes[0].left_first : 0u;

@@ -60,12 +60,11 @@ def test_cuda_matches_committed_golden(mm, noise, scenes, renderer, name):
         assert cnt[k] == v, k
 
 
-@pytest.mark.parametrize("flags_name", ["literal", "shared", "literal_shared", "counters_only", "mux2", "mux3_literal"])
+@pytest.mark.parametrize("flags_name", ["literal", "counters_only", "literal_counters"])
 @pytest.mark.parametrize("name", ["cfg1", "cfg2_small", "maze64", "ref_dispatch"])
 def test_every_kernel_variant_is_bit_identical(mm, oracle, noise, scenes, renderer, name, flags_name):
-    flags = {"literal": mm.FLAG_FORCE_LITERAL, "shared": mm.FLAG_FORCE_SHARED,
-             "literal_shared": mm.FLAG_FORCE_LITERAL | mm.FLAG_FORCE_SHARED, "counters_only": mm.FLAG_COUNTERS,
-             "mux2": mm.FLAG_MUX2, "mux3_literal": mm.FLAG_MUX3 | mm.FLAG_FORCE_LITERAL}[flags_name]
+    flags = {"literal": mm.FLAG_FORCE_LITERAL, "counters_only": mm.FLAG_COUNTERS,
+             "literal_counters": mm.FLAG_FORCE_LITERAL | mm.FLAG_COUNTERS}[flags_name]
     sc, u, p, ch = build_case(mm, name, scenes)
     renderer.upload_scene(sc, noise)
     ref = oracle.render(sc, noise, u, p, ch, debug=True)

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mirror_maze_b200 as mm
 noise = mm.load_noise()
 r = mm.Renderer(0)
-modes = [("exact", 0), ("rcp", mm.FLAG_RCP_SLAB)] if "--rcp" in sys.argv else [("exact", 0), ("smem", mm.FLAG_FORCE_SHARED)]
+modes = [("exact", 0), ("rcp", mm.FLAG_RCP_SLAB)] if "--rcp" in sys.argv else [("exact", 0)]
 mazes = [a for a in sys.argv[1:] if not a.startswith("--")]
 for n in [int(x) for x in (mazes[0] if mazes else "32,64").split(",")]:
     sc = mm.MazeScene(n, 0)
@@ -12,7 +12,6 @@ for n in [int(x) for x in (mazes[0] if mazes else "32,64").split(",")]:
     u = mm.default_uniform(n, 1920, 1080, 4)
     ch = mm.gen_chunks(1920, 1080, 4)
     for name, flags in modes:
-        if n >= 64 and flags == mm.FLAG_FORCE_SHARED: continue
         p = mm.full_frame_params(u, spp=16, bounce_limit=8, flags=flags)
         best = 1e9
         for it in range(4):
