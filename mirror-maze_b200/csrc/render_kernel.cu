@@ -253,8 +253,9 @@ constexpr uint32_t kInnerReps = MM_INNER_REPS;
 struct Hit { float t; uint32_t slot; };
 template <bool MIXED, bool CNT, bool RCP>
 __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const RectI *__restrict__ rects, uint32_t root, bool alive,
-                                     bool lit, V3 ori, V3 dir, float beam_t, uint32_t beam_slot, uint32_t *stack, Tally *tlp) {
+                                     bool lit, V3 ori, V3 dir, float beam_t, uint32_t beam_slot, Tally *tlp) {
     Tally tl = {0u, 0u, 0u, 0u};
+    uint32_t stack[MM_MAX_STACK];              // local memory (L1); BVH depth is validated against it at upload
     const float rx = __frcp_rn(dir.x), ry = __frcp_rn(dir.y), rz = __frcp_rn(dir.z);
     const float rlx = fmul(__fmaf_rn(-dir.x, rx, 1.0f), rx), rly = fmul(__fmaf_rn(-dir.y, ry, 1.0f), ry),
                 rlz = fmul(__fmaf_rn(-dir.z, rz, 1.0f), rz);
@@ -329,7 +330,6 @@ trace_kernel(const __grid_constant__ KParams P) {
 
     const uint64_t path = (uint64_t)blockIdx.x * kBlockThreads + threadIdx.x;
     const bool active = path < P.total_paths;
-    uint32_t stack[MM_MAX_STACK];
     Tally tl = {0u, 0u, 0u, 0u};
     uint32_t seg = 0, nhits = 0, nliteral = 0;
     V3 sample = mk(0.0f, 0.0f, 0.0f);
@@ -396,11 +396,11 @@ trace_kernel(const __grid_constant__ KParams P) {
             const bool any_lit = __any_sync(0xFFFFFFFFu, alive && lit);
             Hit h;
             if (P.rcp_mode) {
-                if (!any_lit) h = traverse<false, CNT, true>(P.pairs, P.rects, root, alive, false, ori, dir, t, slot, stack, &tl);
-                else h = traverse<true, CNT, true>(P.pairs, P.rects, root, alive, lit, ori, dir, t, slot, stack, &tl);
+                if (!any_lit) h = traverse<false, CNT, true>(P.pairs, P.rects, root, alive, false, ori, dir, t, slot, &tl);
+                else h = traverse<true, CNT, true>(P.pairs, P.rects, root, alive, lit, ori, dir, t, slot, &tl);
             } else {
-                if (!any_lit) h = traverse<false, CNT, false>(P.pairs, P.rects, root, alive, false, ori, dir, t, slot, stack, &tl);
-                else h = traverse<true, CNT, false>(P.pairs, P.rects, root, alive, lit, ori, dir, t, slot, stack, &tl);
+                if (!any_lit) h = traverse<false, CNT, false>(P.pairs, P.rects, root, alive, false, ori, dir, t, slot, &tl);
+                else h = traverse<true, CNT, false>(P.pairs, P.rects, root, alive, lit, ori, dir, t, slot, &tl);
             }
             t = h.t; slot = h.slot;
             if (alive) {
