@@ -124,6 +124,14 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1,
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 
+// 32-byte read-only load (LDG.E.256, sm_100+): one instruction and one L1 request per half record.
+struct Line32 { f2 x, y, z, w; };
+__device__ __forceinline__ Line32 ldg256(const void *p) {
+    Line32 q;
+    asm("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(q.x), "=l"(q.y), "=l"(q.z), "=l"(q.w) : "l"(p));
+    return q;
+}
+
 // Per-ray constants of the packed slab test: x and y share register pairs, z is duplicated.
 struct RayK {
     f2 no_xy, nd_xy, r_xy, rl_xy;   // (-o.x, -o.y), (-d.x, -d.y), (r.x, r.y), (rl.x, rl.y)
@@ -237,6 +245,9 @@ __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 or
 // reference's sequence of visits for its own ray; only the interleaving between lanes changes.  (A plain while-while
 // loop — all lanes descend to a leaf, then all test — left 12 of 32 lanes active in the interior body; see profiles/.)
 // `lit` lanes (operands outside the guarded ranges, or MM_FLAG_FORCE_LITERAL) use the general slab form.
+#ifndef MM_LD256
+#define MM_LD256 1
+#endif
 #ifndef MM_LEAF_WEIGHT
 #define MM_LEAF_WEIGHT 4
 #endif
@@ -262,10 +273,10 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
     RayK k;
     k.no_xy = pack2(-ori.x, -ori.y); k.nd_xy = pack2(-dir.x, -dir.y); k.r_xy = pack2(rx, ry); k.rl_xy = pack2(rlx, rly);
     k.no_zz = pack2(-ori.z, -ori.z); k.nd_zz = pack2(-dir.z, -dir.z); k.r_zz = pack2(rz, rz); k.rl_zz = pack2(rlz, rlz);
-    // per-ray record pointers with the travel order folded in: A|B at +0 (x up) / +32 (x down), Z at +64 (z up) / +80 (z down)
+    // per-ray record pointers with the travel order folded in: A|B at +0 (x up) / +32 (x down), Z|link at +64 (z up) / +96 (z down)
     const char *base = reinterpret_cast<const char *>(pairs);
     const char *pAB = base + ((!lit && dir.x < 0.0f) ? 32 : 0);
-    const char *pZ = base + 64 + ((!lit && dir.z < 0.0f) ? 16 : 0);
+    const char *pZ = base + 64 + ((!lit && dir.z < 0.0f) ? 32 : 0);
     asm("" : "+l"(pAB)); asm("" : "+l"(pZ));      // keep them live: ptxas otherwise re-derives them from sign(dir) at every node
     uint32_t cur = alive ? root : CUR_END, head = 0, slot = beam_slot;
     float t = beam_t;
@@ -279,14 +290,29 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
             for (uint32_t rep = 0; rep < kInnerReps; rep++) {
                 if ((cur >> 24) == 0u) {
                     const size_t off = (size_t)cur * sizeof(PairRec);
-                    const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(base + 96 + off));
                     if (CNT) tl.inner++;
                     if (!MIXED || !lit) {
+#if MM_LD256 == 2
+                        const Line32 ab = ldg256(pAB + off), zl = ldg256(pZ + off);
+                        ulonglong2 A, B, Z;
+                        A.x = ab.x; A.y = ab.y; B.x = ab.z; B.y = ab.w; Z.x = zl.x; Z.y = zl.y;
+                        uint2 lk;
+                        asm("mov.b64 {%0, %1}, %2;" : "=r"(lk.x), "=r"(lk.y) : "l"(zl.z));
+#elif MM_LD256 == 1
+                        const Line32 ab = ldg256(pAB + off);
+                        ulonglong2 A, B;
+                        A.x = ab.x; A.y = ab.y; B.x = ab.z; B.y = ab.w;
+                        const ulonglong2 Z = __ldg(reinterpret_cast<const ulonglong2 *>(pZ + off));
+                        const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(pZ + off + 16));
+#else
                         const ulonglong2 A = __ldg(reinterpret_cast<const ulonglong2 *>(pAB + off));
                         const ulonglong2 B = __ldg(reinterpret_cast<const ulonglong2 *>(pAB + off + 16));
                         const ulonglong2 Z = __ldg(reinterpret_cast<const ulonglong2 *>(pZ + off));
+                        const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(pZ + off + 16));
+#endif
                         inner_step_packed<CNT, RCP>(A, B, Z, lk, k, t, cur, head, stack, tl);
                     } else {
+                        const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(base + 80 + off));
                         const float4 a = __ldg(reinterpret_cast<const float4 *>(base + off)), b = __ldg(reinterpret_cast<const float4 *>(base + off + 16));
                         const float4 zu = __ldg(reinterpret_cast<const float4 *>(base + off + 64));
                         Axis ax, ay, az;
@@ -606,7 +632,7 @@ __global__ void __launch_bounds__(256) blur_kernel(const float4 *__restrict__ sr
 }
 
 // Micro-benchmarks for the two rooflines the path is measured against (SURVEY §8 d): how fast can this GPU fetch 56 useful
-// bytes (three 16-B loads + one 8-B load, the traversal's per-visit pattern) from random 128-B records of a table of the
+// bytes (a 32-B, a 16-B and an 8-B load, the traversal's per-visit pattern) from random 128-B records of a table of the
 // scene's size, and how fast can it issue FP32 FMAs.  Independent addresses / chains: these are peaks, not models.
 __global__ void __launch_bounds__(256) mb_gather_kernel(const float4 *__restrict__ table, uint32_t n_records, uint32_t iters,
                                                         float *__restrict__ sink) {
@@ -615,10 +641,11 @@ __global__ void __launch_bounds__(256) mb_gather_kernel(const float4 *__restrict
     for (uint32_t i = 0; i < iters; i++) {
         idx = idx * 747796405u + 2891336453u;
         const float4 *rec = table + (size_t)((idx >> 8) % n_records) * 8;
-        const uint32_t down = (idx & 1u) * 4u;                                  // either travel order, like the kernel
-        const float4 a = __ldg(rec + down), b = __ldg(rec + 1 + down), c = __ldg(rec + 2 + down);
-        const float2 l = __ldg(reinterpret_cast<const float2 *>(rec + 3));
-        acc += a.x + a.w + b.y + c.z + l.x;
+        const uint32_t down = (idx & 1u) * 2u;                                  // either travel order, like the kernel
+        const Line32 ab = ldg256(rec + down);
+        const float4 z = __ldg(rec + 4 + down);
+        const float2 l = __ldg(reinterpret_cast<const float2 *>(rec + 5 + down));
+        acc += lo2f(ab.x) + hi2f(ab.y) + lo2f(ab.w) + z.z + l.x;
     }
     if (acc == 12345.678f) sink[0] = acc;                                       // keep the loads alive
 }

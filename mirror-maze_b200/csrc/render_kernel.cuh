@@ -13,13 +13,14 @@ namespace mmk {
 //   a_xu = (c0.min.x, c0.min.y, c0.max.x, c0.max.y)   b_xu = the same for child 1          (rays with dir.x > 0)
 //   a_xd = (c0.max.x, c0.min.y, c0.min.x, c0.max.y)   b_xd = the same for child 1          (rays with dir.x < 0)
 //   z_u  = (c0.min.z, c1.min.z, c0.max.z, c1.max.z)   z_d = (c0.max.z, c1.max.z, c0.min.z, c1.min.z)
-//   link = (c0.desc, c1.desc, 0, 0) with desc = link | count << 24: count > 0 is a leaf whose link is the first slot in the
-//   leaf-ordered rect array, count == 0 an interior node whose link is its pair index.
-// One traversal step = two adjacent 16-B loads (a, b) + one 16-B load (z) + one 8-B load (link) from one line.
-struct __align__(16) PairRec {
-    float4 a_xu, b_xu, a_xd, b_xd, z_u, z_d;
-    uint4 link;
-    uint4 pad;
+//   link_u = link_d = (c0.desc, c1.desc, 0, 0) with desc = link | count << 24: count > 0 is a leaf whose link is the first
+//   slot in the leaf-ordered rect array, count == 0 an interior node whose link is its pair index.  The link is stored
+//   behind each z order so that (z, link) is one aligned 32-B unit.
+// One traversal step reads 56 B of one line: (a, b) in the ray's x order as one 32-B load (LDG.256), then z and link in its z order.
+struct __align__(32) PairRec {
+    float4 a_xu, b_xu, a_xd, b_xd;
+    float4 z_u; uint4 link_u;
+    float4 z_d; uint4 link_d;
 };
 static_assert(sizeof(PairRec) == 128, "pair record is 128 B");
 

@@ -59,7 +59,7 @@ int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *
         p.b_xd = make_float4(b.aabb_max.x, b.aabb_min.y, b.aabb_min.x, b.aabb_max.y);
         p.z_u = make_float4(a.aabb_min.z, b.aabb_min.z, a.aabb_max.z, b.aabb_max.z);
         p.z_d = make_float4(a.aabb_max.z, b.aabb_max.z, a.aabb_min.z, b.aabb_min.z);
-        p.link = make_uint4(desc(nodes[i].left_first), desc(nodes[i].left_first + 1), 0u, 0u);
+        p.link_u = p.link_d = make_uint4(desc(nodes[i].left_first), desc(nodes[i].left_first + 1), 0u, 0u);
         const float c[12] = {a.aabb_min.x, a.aabb_min.y, a.aabb_min.z, a.aabb_max.x, a.aabb_max.y, a.aabb_max.z,
                              b.aabb_min.x, b.aabb_min.y, b.aabb_min.z, b.aabb_max.x, b.aabb_max.y, b.aabb_max.z};
         for (int k = 0; k < 12; k++) fast_ok = fast_ok && coord_ok(c[k]);
