@@ -306,7 +306,7 @@ def run_ours(a):
     issue_peak_now = info["n_sms"] * 128 * sm_now * 1e6 / 1e12            # at the clock seen under load
     achieved_tops = ops_per_launch / (kernel_mean_ms * 1e-3) / 1e12 if kernel_mean_ms else 0.0
     # measured peaks of the two binding rooflines (micro-benchmarks in the library; untimed, after the measurement)
-    pair_table_bytes = max(128, (info["n_nodes"] - 1) // 2 * 128)
+    pair_table_bytes = max(192, (info["n_nodes"] - 1) // 2 * 192)           # 192-B pair records
     gather_peak = r.microbench(0, pair_table_bytes)            # GB/s of the per-visit fetch pattern from a table of the scene's size
     ffma_peak = r.microbench(1)                                # T FP32 FMA lane-instr/s
     node_bytes = (64 * cnt_frame["inner_visits"] + 52 * cnt_frame["rect_tests"]) / world

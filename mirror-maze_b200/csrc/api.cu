@@ -413,11 +413,11 @@ int mm_microbench(mm_ctx *ctx, int kind, uint64_t table_bytes, double *result) {
     float *sink = reinterpret_cast<float *>(ctx->d_counters);
     float ms = 0.0f;
     if (kind == MM_MICROBENCH_GATHER) {
-        if (table_bytes < 128) return fail(ctx, MM_ERR_INVALID, "mm_microbench: table smaller than one record");
-        const uint32_t n_records = (uint32_t)(table_bytes / 128 > 0x7FFFFFFFull ? 0x7FFFFFFFull : table_bytes / 128);
+        if (table_bytes < sizeof(PairRec)) return fail(ctx, MM_ERR_INVALID, "mm_microbench: table smaller than one record");
+        const uint32_t n_records = (uint32_t)(table_bytes / sizeof(PairRec) > 0x7FFFFFFFull ? 0x7FFFFFFFull : table_bytes / sizeof(PairRec));
         void *table = nullptr;
-        CK(cudaMalloc(&table, (size_t)n_records * 128));
-        cudaError_t e = cudaMemsetAsync(table, 0, (size_t)n_records * 128, ctx->stream);
+        CK(cudaMalloc(&table, (size_t)n_records * sizeof(PairRec)));
+        cudaError_t e = cudaMemsetAsync(table, 0, (size_t)n_records * sizeof(PairRec), ctx->stream);
         const uint32_t iters = 4096;
         if (e == cudaSuccess) e = launch_mb_gather(table, n_records, 256, blocks, sink, ctx->stream);      // warm-up
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev0, ctx->stream);

@@ -173,20 +173,19 @@ __device__ __forceinline__ void descend(float lo1, float hi1, float lo2, float h
 }
 
 // One interior visit, fast form (guarded operand ranges: no zero / NaN / inf anywhere).  The quotients are the exact
-// RN((b - o)/d) of the literal code; the record is loaded with x and z in the ray's travel order, so their near plane is
-// the first and their far plane the second value (rounding is monotone), y keeps the literal min/max:
-//   A = (c0.near.x, c0.min.y | c0.far.x, c0.max.y)   B likewise for child 1   Z = (c0.near.z, c1.near.z | c0.far.z, c1.far.z)
+// RN((b - o)/d) of the literal code; the record is loaded in the ray's travel order on every axis, so each axis' near
+// plane is the first and its far plane the second value (rounding is monotone: min(t1,t2) is the near plane's quotient):
+//   A = (c0.near.x, c0.near.y | c0.far.x, c0.far.y)   B likewise for child 1   Z = (c0.near.z, c1.near.z | c0.far.z, c1.far.z)
 template <bool CNT, bool RCP>
 __device__ __forceinline__ void inner_step_packed(const ulonglong2 &A, const ulonglong2 &B, const ulonglong2 &Z, const uint2 &lk,
                                                   const RayK &k, float t, uint32_t &cur, uint32_t &head, uint32_t *stack, Tally &tl) {
     const f2 an = quot2<RCP>(A.x, k.no_xy, k.nd_xy, k.r_xy, k.rl_xy), af = quot2<RCP>(A.y, k.no_xy, k.nd_xy, k.r_xy, k.rl_xy);
     const f2 bn = quot2<RCP>(B.x, k.no_xy, k.nd_xy, k.r_xy, k.rl_xy), bf = quot2<RCP>(B.y, k.no_xy, k.nd_xy, k.r_xy, k.rl_xy);
     const f2 zn = quot2<RCP>(Z.x, k.no_zz, k.nd_zz, k.r_zz, k.rl_zz), zf = quot2<RCP>(Z.y, k.no_zz, k.nd_zz, k.r_zz, k.rl_zz);
-    const float a1 = hi2f(an), a2 = hi2f(af), b1 = hi2f(bn), b2 = hi2f(bf);
-    const float lo1 = fmaxf(fmaxf(lo2f(an), fminf(a1, a2)), lo2f(zn));
-    const float hi1 = fminf(fminf(lo2f(af), fmaxf(a1, a2)), lo2f(zf));
-    const float lo2 = fmaxf(fmaxf(lo2f(bn), fminf(b1, b2)), hi2f(zn));
-    const float hi2 = fminf(fminf(lo2f(bf), fmaxf(b1, b2)), hi2f(zf));
+    const float lo1 = fmaxf(fmaxf(lo2f(an), hi2f(an)), lo2f(zn));
+    const float hi1 = fminf(fminf(lo2f(af), hi2f(af)), lo2f(zf));
+    const float lo2 = fmaxf(fmaxf(lo2f(bn), hi2f(bn)), hi2f(zn));
+    const float hi2 = fminf(fminf(lo2f(bf), hi2f(bf)), hi2f(zf));
     descend<CNT>(lo1, hi1, lo2, hi2, lk, t, cur, head, stack, tl);
 }
 
@@ -216,7 +215,7 @@ __device__ __forceinline__ void inner_step_general(const float4 &a, const float4
 template <bool CNT>
 __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 ori, V3 dir, float &t, uint32_t &slot, uint32_t &cur,
                                           uint32_t &head, const uint32_t *stack, Tally &tl) {
-    const uint32_t first = cur & 0xFFFFFFu, count = cur >> 24;
+    const uint32_t first = cur & 0xFFFFFFu, count = (cur >> 24) & 0x7Fu;
     for (uint32_t i = 0; i < count; i++) {
         const float4 *rp = reinterpret_cast<const float4 *>(rects + first + i);
         const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
@@ -273,23 +272,23 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
     RayK k;
     k.no_xy = pack2(-ori.x, -ori.y); k.nd_xy = pack2(-dir.x, -dir.y); k.r_xy = pack2(rx, ry); k.rl_xy = pack2(rlx, rly);
     k.no_zz = pack2(-ori.z, -ori.z); k.nd_zz = pack2(-dir.z, -dir.z); k.r_zz = pack2(rz, rz); k.rl_zz = pack2(rlz, rlz);
-    // per-ray record pointers with the travel order folded in: A|B at +0 (x up) / +32 (x down), Z|link at +64 (z up) / +96 (z down)
+    // per-ray record pointers with the travel order folded in: ab[sx + 2 sy] at +32 (sx + 2 sy), z|link[sz] at +128 + 32 sz
     const char *base = reinterpret_cast<const char *>(pairs);
-    const char *pAB = base + ((!lit && dir.x < 0.0f) ? 32 : 0);
-    const char *pZ = base + 64 + ((!lit && dir.z < 0.0f) ? 32 : 0);
+    const char *pAB = base + (lit ? 0 : (dir.x < 0.0f ? 32 : 0) + (dir.y < 0.0f ? 64 : 0));
+    const char *pZ = base + 128 + ((!lit && dir.z < 0.0f) ? 32 : 0);
     asm("" : "+l"(pAB)); asm("" : "+l"(pZ));      // keep them live: ptxas otherwise re-derives them from sign(dir) at every node
     uint32_t cur = alive ? root : CUR_END, head = 0, slot = beam_slot;
     float t = beam_t;
     while (true) {
-        const bool isI = (cur >> 24) == 0u;
+        const bool isI = (cur & kLeafBit) == 0u;
         const bool isL = !isI && cur != CUR_END;
         const unsigned mI = __ballot_sync(0xFFFFFFFFu, isI), mL = __ballot_sync(0xFFFFFFFFu, isL);
         if ((mI | mL) == 0u) break;
         if (mI != 0u && __popc(mI) >= kLeafWeight * __popc(mL)) {
 #pragma unroll 1
             for (uint32_t rep = 0; rep < kInnerReps; rep++) {
-                if ((cur >> 24) == 0u) {
-                    const size_t off = (size_t)cur * sizeof(PairRec);
+                if ((cur & kLeafBit) == 0u) {
+                    const size_t off = cur;                      // interior descriptors are byte offsets
                     if (CNT) tl.inner++;
                     if (!MIXED || !lit) {
 #if MM_LD256 == 2
@@ -312,9 +311,9 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
 #endif
                         inner_step_packed<CNT, RCP>(A, B, Z, lk, k, t, cur, head, stack, tl);
                     } else {
-                        const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(base + 80 + off));
+                        const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(base + 144 + off));
                         const float4 a = __ldg(reinterpret_cast<const float4 *>(base + off)), b = __ldg(reinterpret_cast<const float4 *>(base + off + 16));
-                        const float4 zu = __ldg(reinterpret_cast<const float4 *>(base + off + 64));
+                        const float4 zu = __ldg(reinterpret_cast<const float4 *>(base + off + 128));
                         Axis ax, ay, az;
                         ax.o = ori.x; ax.d = dir.x; ax.r = rx; ax.rl = rlx;
                         ay.o = ori.y; ay.d = dir.y; ay.r = ry; ay.rl = rly;
@@ -360,7 +359,7 @@ trace_kernel(const __grid_constant__ KParams P) {
     uint32_t seg = 0, nhits = 0, nliteral = 0;
     V3 sample = mk(0.0f, 0.0f, 0.0f);
     uint32_t pxx = 0, pxy = 0, k = 0, flat = 0;
-    const uint32_t root = P.root_link | (P.root_count << 24);
+    const uint32_t root = P.root_count ? (kLeafBit | P.root_link | (P.root_count << 24)) : P.root_link;   // pair 0 is at byte offset 0
     V3 st_ori = mk(0.0f, 0.0f, 0.0f), st_dir = mk(1.0f, 1.0f, 1.0f), st_color = mk(1.0f, 1.0f, 1.0f), st_light = mk(0.0f, 0.0f, 0.0f);
     float st_t = 1e30f;
     uint32_t st_slot = 0xFFFFFFFFu, st_state = 0u, first_hit = 0xFFFFFFFFu;
@@ -640,11 +639,11 @@ __global__ void __launch_bounds__(256) mb_gather_kernel(const float4 *__restrict
     float acc = 0.0f;
     for (uint32_t i = 0; i < iters; i++) {
         idx = idx * 747796405u + 2891336453u;
-        const float4 *rec = table + (size_t)((idx >> 8) % n_records) * 8;
-        const uint32_t down = (idx & 1u) * 2u;                                  // either travel order, like the kernel
-        const Line32 ab = ldg256(rec + down);
-        const float4 z = __ldg(rec + 4 + down);
-        const float2 l = __ldg(reinterpret_cast<const float2 *>(rec + 5 + down));
+        const float4 *rec = table + (size_t)((idx >> 8) % n_records) * 12;
+        const uint32_t sxy = (idx & 3u) * 2u, sz = ((idx >> 2) & 1u) * 2u;      // any travel order, like the kernel
+        const Line32 ab = ldg256(rec + sxy);
+        const float4 z = __ldg(rec + 8 + sz);
+        const float2 l = __ldg(reinterpret_cast<const float2 *>(rec + 9 + sz));
         acc += lo2f(ab.x) + hi2f(ab.y) + lo2f(ab.w) + z.z + l.x;
     }
     if (acc == 12345.678f) sink[0] = acc;                                       // keep the loads alive

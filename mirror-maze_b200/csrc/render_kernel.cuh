@@ -6,23 +6,24 @@
 
 namespace mmk {
 
-// One interior node's two children, 128 B = one L1/L2 line.
+// One interior node's two children, 192 B.
 // The reference node array (32 B each, children adjacent; shaders.metal:30-35,134-135) is re-laid per interior node for the
-// packed-FP32 slab test: x and y of a plane sit in adjacent words (one register pair after the load), x and z come in both
-// travel orders so that the near plane is always the first value, y keeps (min, max):
-//   a_xu = (c0.min.x, c0.min.y, c0.max.x, c0.max.y)   b_xu = the same for child 1          (rays with dir.x > 0)
-//   a_xd = (c0.max.x, c0.min.y, c0.min.x, c0.max.y)   b_xd = the same for child 1          (rays with dir.x < 0)
-//   z_u  = (c0.min.z, c1.min.z, c0.max.z, c1.max.z)   z_d = (c0.max.z, c1.max.z, c0.min.z, c1.min.z)
-//   link_u = link_d = (c0.desc, c1.desc, 0, 0) with desc = link | count << 24: count > 0 is a leaf whose link is the first
-//   slot in the leaf-ordered rect array, count == 0 an interior node whose link is its pair index.  The link is stored
-//   behind each z order so that (z, link) is one aligned 32-B unit.
-// One traversal step reads 56 B of one line: (a, b) in the ray's x order as one 32-B load (LDG.256), then z and link in its z order.
+// packed-FP32 slab test: x and y of a plane sit in adjacent words (one register pair after the load) and every axis is
+// stored in both travel orders, so that whatever the ray's direction signs the near plane is the first value:
+//   ab[sx + 2*sy] = (c0.near.x, c0.near.y, c0.far.x, c0.far.y,  c1.near.x, c1.near.y, c1.far.x, c1.far.y)
+//                   with near = min, far = max on an axis the ray travels up (s = 0), swapped when it travels down (s = 1)
+//   z[sz]         = (c0.near.z, c1.near.z, c0.far.z, c1.far.z),  link[sz] = (c0.desc, c1.desc, 0, 0)   (same link in both)
+//   desc: interior child = byte offset of its record (pair index * 192, < 2^31);
+//         leaf child     = 0x80000000 | count << 24 | first slot in the leaf-ordered rect array (count <= 126).
+// ab[0] / z[0] are the reference's (min, max) order, which the general (literal) slab form reads.
+// One traversal step reads 56 B: ab[s] as one 32-B load (LDG.256), then z[sz] (16 B) and link (8 B).
 struct __align__(32) PairRec {
-    float4 a_xu, b_xu, a_xd, b_xd;
-    float4 z_u; uint4 link_u;
-    float4 z_d; uint4 link_d;
+    float4 ab[4][2];
+    struct { float4 z; uint4 link; } zl[2];
 };
-static_assert(sizeof(PairRec) == 128, "pair record is 128 B");
+static_assert(sizeof(PairRec) == 192, "pair record is 192 B");
+constexpr uint32_t kLeafBit = 0x80000000u;
+constexpr uint32_t kMaxLeafCount = 126;
 
 // One rectangle in leaf order (slot s = position in the reference `indices` array), 64 B.
 // The normal and the edge lengths are per-rect constants of ray_rect_intersect (shaders.metal:52,60-61); they are

@@ -30,8 +30,8 @@ int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *
         err = "BVH depth " + std::to_string(depth) + " exceeds MM_MAX_STACK";
         return MM_ERR_BVH;
     }
-    if (max_leaf > 255 || n_planes >= (1u << 24) || n_nodes >= (1u << 24)) {
-        err = "scene exceeds packed-descriptor limits (leaf > 255 planes or >= 2^24 planes/nodes)";
+    if (max_leaf > kMaxLeafCount || n_planes >= (1u << 24) || n_nodes >= (1u << 24)) {
+        err = "scene exceeds packed-descriptor limits (leaf > 126 planes or >= 2^24 planes/nodes)";
         return MM_ERR_UNSUPPORTED;
     }
     for (uint32_t i = 0; i < n_planes; i++)
@@ -44,7 +44,7 @@ int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *
         if (nodes[i].tri_count == 0) pair_id[i] = n_pairs++;
     auto desc = [&](uint32_t c) -> uint32_t {
         const mm_bvh_node &nd = nodes[c];
-        return nd.tri_count > 0 ? (nd.left_first | (nd.tri_count << 24)) : pair_id[c];
+        return nd.tri_count > 0 ? (kLeafBit | nd.left_first | (nd.tri_count << 24)) : pair_id[c] * (uint32_t)sizeof(PairRec);
     };
     out.pairs.assign(n_pairs ? n_pairs : 1, PairRec());
     std::memset(out.pairs.data(), 0, out.pairs.size() * sizeof(PairRec));
@@ -53,13 +53,17 @@ int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *
         if (nodes[i].tri_count != 0) continue;
         const mm_bvh_node &a = nodes[nodes[i].left_first], &b = nodes[nodes[i].left_first + 1];
         PairRec &p = out.pairs[pair_id[i]];
-        p.a_xu = make_float4(a.aabb_min.x, a.aabb_min.y, a.aabb_max.x, a.aabb_max.y);
-        p.b_xu = make_float4(b.aabb_min.x, b.aabb_min.y, b.aabb_max.x, b.aabb_max.y);
-        p.a_xd = make_float4(a.aabb_max.x, a.aabb_min.y, a.aabb_min.x, a.aabb_max.y);
-        p.b_xd = make_float4(b.aabb_max.x, b.aabb_min.y, b.aabb_min.x, b.aabb_max.y);
-        p.z_u = make_float4(a.aabb_min.z, b.aabb_min.z, a.aabb_max.z, b.aabb_max.z);
-        p.z_d = make_float4(a.aabb_max.z, b.aabb_max.z, a.aabb_min.z, b.aabb_min.z);
-        p.link_u = p.link_d = make_uint4(desc(nodes[i].left_first), desc(nodes[i].left_first + 1), 0u, 0u);
+        for (int sy = 0; sy < 2; sy++)
+            for (int sx = 0; sx < 2; sx++) {
+                const mm_bvh_node *ch[2] = {&a, &b};
+                for (int k = 0; k < 2; k++) {
+                    const mm_float3 &mn = ch[k]->aabb_min, &mx = ch[k]->aabb_max;
+                    p.ab[sx + 2 * sy][k] = make_float4(sx ? mx.x : mn.x, sy ? mx.y : mn.y, sx ? mn.x : mx.x, sy ? mn.y : mx.y);
+                }
+            }
+        p.zl[0].z = make_float4(a.aabb_min.z, b.aabb_min.z, a.aabb_max.z, b.aabb_max.z);
+        p.zl[1].z = make_float4(a.aabb_max.z, b.aabb_max.z, a.aabb_min.z, b.aabb_min.z);
+        p.zl[0].link = p.zl[1].link = make_uint4(desc(nodes[i].left_first), desc(nodes[i].left_first + 1), 0u, 0u);
         const float c[12] = {a.aabb_min.x, a.aabb_min.y, a.aabb_min.z, a.aabb_max.x, a.aabb_max.y, a.aabb_max.z,
                              b.aabb_min.x, b.aabb_min.y, b.aabb_min.z, b.aabb_max.x, b.aabb_max.y, b.aabb_max.z};
         for (int k = 0; k < 12; k++) fast_ok = fast_ok && coord_ok(c[k]);
