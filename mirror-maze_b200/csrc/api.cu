@@ -40,7 +40,7 @@ struct mm_ctx {
     float *d_dbg_rad = nullptr;
     size_t dbg_cap = 0;
     // last launch facts
-    uint32_t last_smem = 0, last_blocks_per_sm = 0;
+    uint32_t last_smem = 0, last_blocks_per_sm = 0, last_block_threads = 0;
     const void *cfg_fn = nullptr;     // kernel variant whose attributes / occupancy were last set up
     size_t cfg_smem = 0;
 };
@@ -231,8 +231,10 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
 
     L.choice.debug = debug;
     L.choice.counters = debug || (par->flags & MM_FLAG_COUNTERS);
-    L.smem = 3 * kBlockThreads * sizeof(float);                          // reduction scratch
-    const uint64_t blocks = (p.total_paths + kBlockThreads - 1) / kBlockThreads;
+    const int bt = block_threads_for(p.spp);
+    L.choice.block_threads = bt;
+    L.smem = 3 * (size_t)bt * sizeof(float);                             // reduction scratch
+    const uint64_t blocks = (p.total_paths + (uint64_t)bt - 1) / (uint64_t)bt;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, MM_ERR_UNSUPPORTED, "too many paths for one launch");
     L.blocks = (unsigned)blocks;
     return MM_OK;
@@ -243,11 +245,11 @@ int do_launch(mm_ctx *ctx, Launch &L) {
     if (fn != ctx->cfg_fn || L.smem != ctx->cfg_smem) {   // once per kernel variant, not per frame
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlockThreads, L.smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, L.choice.block_threads, L.smem));
         ctx->last_blocks_per_sm = (uint32_t)per_sm;
         ctx->cfg_fn = fn; ctx->cfg_smem = L.smem;
     }
-    ctx->last_smem = (uint32_t)L.smem;
+    ctx->last_smem = (uint32_t)L.smem; ctx->last_block_threads = (uint32_t)L.choice.block_threads;
     CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(launch_trace(L.p, L.choice, L.blocks, L.smem, ctx->stream));
@@ -483,7 +485,7 @@ int mm_get_scene_info(mm_ctx *ctx, mm_scene_info *out) {
     out->n_planes = ctx->n_slots; out->n_nodes = ctx->n_nodes; out->bvh_depth = ctx->depth; out->max_leaf = ctx->max_leaf;
     out->nodes_in_shared = 0u;   // child pairs are read through L1 (a shared-memory copy measured slower, profiles/r1_sched_sweep.txt)
     out->fast_slab_ok = ctx->fast_ok ? 1u : 0u;
-    out->smem_bytes = ctx->last_smem; out->block_threads = kBlockThreads; out->blocks_per_sm = ctx->last_blocks_per_sm;
+    out->smem_bytes = ctx->last_smem; out->block_threads = ctx->last_block_threads; out->blocks_per_sm = ctx->last_blocks_per_sm;
     out->n_sms = (uint32_t)ctx->n_sms;
     return MM_OK;
 }

@@ -247,6 +247,9 @@ __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 or
 #ifndef MM_LD256
 #define MM_LD256 1
 #endif
+#ifndef MM_UNROLL_REPS
+#define MM_UNROLL_REPS 0
+#endif
 #ifndef MM_LEAF_WEIGHT
 #define MM_LEAF_WEIGHT 4
 #endif
@@ -285,7 +288,11 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
         const unsigned mI = __ballot_sync(0xFFFFFFFFu, isI), mL = __ballot_sync(0xFFFFFFFFu, isL);
         if ((mI | mL) == 0u) break;
         if (mI != 0u && __popc(mI) >= kLeafWeight * __popc(mL)) {
+#if MM_UNROLL_REPS
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (uint32_t rep = 0; rep < kInnerReps; rep++) {
                 if ((cur & kLeafBit) == 0u) {
                     const size_t off = cur;                      // interior descriptors are byte offsets
@@ -347,8 +354,8 @@ __device__ __forceinline__ void sample_noise_xy(const uint8_t *noise, uint32_t n
     ny = fdiv((float)c.y, 255.0f);
 }
 
-template <bool CNT, bool DBG>
-__global__ void __launch_bounds__(kBlockThreads, MM_MIN_BLOCKS)
+template <bool CNT, bool DBG, int kBlockThreads>
+__global__ void __launch_bounds__(kBlockThreads, 1024 / kBlockThreads)
 trace_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *red = reinterpret_cast<float *>(smem_raw);                      // 3 * kBlockThreads floats
@@ -660,19 +667,22 @@ __global__ void __launch_bounds__(256) mb_ffma_kernel(uint32_t iters, float *__r
 }
 
 template <bool C, bool D>
-const void *kptr() { return reinterpret_cast<const void *>(&trace_kernel<C, D>); }
+const void *kptr(int bt) {
+    return bt == kSmallBlock ? reinterpret_cast<const void *>(&trace_kernel<C, D, kSmallBlock>)
+                             : reinterpret_cast<const void *>(&trace_kernel<C, D, kLargeBlock>);
+}
 
 }  // namespace
 
 const void *kernel_ptr(KernelChoice c) {
-    if (c.debug) return kptr<true, true>();
-    return c.counters ? kptr<true, false>() : kptr<false, false>();
+    if (c.debug) return kptr<true, true>(c.block_threads);
+    return c.counters ? kptr<true, false>(c.block_threads) : kptr<false, false>(c.block_threads);
 }
 
 cudaError_t launch_trace(const KParams &p, KernelChoice c, unsigned blocks, size_t smem_bytes, cudaStream_t stream) {
     const void *fn = kernel_ptr(c);
     void *args[] = {const_cast<KParams *>(&p)};
-    return cudaLaunchKernel(fn, dim3(blocks), dim3(kBlockThreads), args, smem_bytes, stream);
+    return cudaLaunchKernel(fn, dim3(blocks), dim3(c.block_threads), args, smem_bytes, stream);
 }
 
 cudaError_t launch_mb_gather(const void *table, uint32_t n_records, uint32_t iters, unsigned blocks, float *sink, cudaStream_t stream) {

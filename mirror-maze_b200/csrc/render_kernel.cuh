@@ -75,16 +75,18 @@ struct KParams {
     float *dbg_radiance;
 };
 
-#ifndef MM_BLOCK_THREADS
-#define MM_BLOCK_THREADS 256
+// Block shapes: 32 warps/SM at <= 64 registers either way.  A block must hold whole pixels (spp | block threads, for the
+// in-block reduction); small blocks retire sooner after their slowest warp (profiles/r1_block_shape.txt), so frames with
+// spp <= kSmallBlock use kSmallBlock threads and only larger sample counts use kLargeBlock.
+#ifndef MM_SMALL_BLOCK
+#define MM_SMALL_BLOCK 64
 #endif
-#ifndef MM_MIN_BLOCKS
-#define MM_MIN_BLOCKS 4
-#endif
-constexpr int kBlockThreads = MM_BLOCK_THREADS;   // 32 warps/SM at <= 64 registers (measured best; profiles/r1_block_shape.txt)
+constexpr int kSmallBlock = MM_SMALL_BLOCK;
+constexpr int kLargeBlock = 256;
+inline int block_threads_for(uint32_t spp) { return spp <= (uint32_t)kSmallBlock ? kSmallBlock : kLargeBlock; }
 
 // Returns the kernel's static properties for the occupancy query and launch.
-struct KernelChoice { bool counters, debug; };
+struct KernelChoice { bool counters, debug; int block_threads; };
 const void *kernel_ptr(KernelChoice c);
 cudaError_t launch_trace(const KParams &p, KernelChoice c, unsigned blocks, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_mb_gather(const void *table, uint32_t n_records, uint32_t iters, unsigned blocks, float *sink, cudaStream_t stream);
