@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--mirror-limit", type=int, default=15)
     ap.add_argument("--cpu-crop", type=int, default=4, help="cpu baseline renders every k-th chunk group")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--flags", type=int, default=0, help="MM_FLAG_* for experiments (2 = literal divides, 4 = nodes in global)")
+    ap.add_argument("--flags", type=int, default=0, help="MM_FLAG_* for experiments (2 = literal divides for every ray, 64 = reciprocal-multiply slab arithmetic)")
     return ap.parse_args()
 
 
