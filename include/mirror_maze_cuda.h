@@ -224,6 +224,15 @@ int mm_microbench(mm_ctx *ctx, int kind, uint64_t table_bytes, double *result);
  */
 int mm_selftest_quotient(mm_ctx *ctx, uint64_t n_pairs, uint64_t seed, uint64_t *mismatches);
 
+/*
+ * Verification hook for the rect edge tests (reference src/shaders.metal:60-63: d = dot(rv, edge) / length(edge),
+ * 0 <= d && d <= length).  The kernel stores, per edge, the interval [lo, up] on x = dot(rv, edge) that decides exactly
+ * what the divide-then-compare decides under IEEE round-to-nearest-even; this returns that interval for a length.
+ * MM_ERR_UNSUPPORTED when the length is outside the guarded range (such a scene renders with the literal divides).
+ * Host-only, no GPU needed.
+ */
+int mm_rect_edge_thresholds(float length, float *lo, float *up);
+
 /* ---- Host surface kept from the reference (restated in C++; no device work) ------------------------- */
 
 /*

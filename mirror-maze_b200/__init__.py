@@ -9,7 +9,7 @@ the CUDA library or a B200 is missing.
 from .abi import (MMError, load_library, library_path, Float2, Float3, Float4, Plane, BVHNode, Camera, Uniform, Chunk,
                   Params, Counters, SceneInfo, FLAG_COUNTERS, FLAG_FORCE_LITERAL, FLAG_RCP_SLAB, MAX_STACK)
 from .host import (MazeScene, StdRng, default_uniform, gen_chunks, calculate_quaternion, update_quat_angle, quat_mult,
-                   load_noise, full_frame_params, check_collision, chacha_block, ChunkBag, move_camera)
+                   load_noise, full_frame_params, check_collision, chacha_block, ChunkBag, move_camera, rect_edge_thresholds)
 from .renderer import Renderer, TiledFrameRenderer, tile_partition
 
 __all__ = [n for n in dir() if not n.startswith("_")]

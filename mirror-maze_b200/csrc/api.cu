@@ -27,7 +27,7 @@ struct mm_ctx {
     RectS *d_shade = nullptr;
     uint8_t *d_noise = nullptr;
     uint32_t n_pairs = 0, n_slots = 0, n_nodes = 0, root_link = 0, root_count = 0, depth = 0, max_leaf = 0, noise_w = 0, noise_h = 0;
-    bool fast_ok = false;
+    bool fast_ok = false, rect_fast_ok = false;
     // per-frame
     mm_chunk *d_chunks = nullptr;
     uint32_t chunks_cap = 0, n_chunks = 0;
@@ -151,7 +151,7 @@ int mm_upload_scene(mm_ctx *ctx, const mm_plane *planes, uint32_t n_planes, cons
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_pairs = prep.n_pairs; ctx->n_slots = n_planes; ctx->n_nodes = n_nodes;
     ctx->root_link = prep.root_link; ctx->root_count = prep.root_count;
-    ctx->depth = prep.depth; ctx->max_leaf = prep.max_leaf; ctx->fast_ok = prep.fast_ok;
+    ctx->depth = prep.depth; ctx->max_leaf = prep.max_leaf; ctx->fast_ok = prep.fast_ok; ctx->rect_fast_ok = prep.rect_fast_ok;
     ctx->noise_w = noise_w; ctx->noise_h = noise_h;
     ctx->have_scene = true;
     return MM_OK;
@@ -224,6 +224,7 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
     p.force_literal = (par->flags & MM_FLAG_FORCE_LITERAL) ? 1u : 0u;
     p.rcp_mode = (par->flags & MM_FLAG_RCP_SLAB) ? 1u : 0u;
     p.scene_fast_ok = ctx->fast_ok ? 1u : 0u;
+    p.rect_fast_ok = (ctx->rect_fast_ok && !(par->flags & MM_FLAG_FORCE_LITERAL)) ? 1u : 0u;
     p.total_paths = (uint64_t)count * T;
     p.pairs = ctx->d_pairs; p.rects = ctx->d_rects; p.shade = ctx->d_shade;
     p.chunks = ctx->d_chunks; p.noise = ctx->d_noise;
@@ -444,6 +445,11 @@ int mm_microbench(mm_ctx *ctx, int kind, uint64_t table_bytes, double *result) {
     }
     ctx->timed = false;
     return MM_OK;
+}
+
+int mm_rect_edge_thresholds(float length, float *lo, float *up) {
+    if (!lo || !up) return MM_ERR_INVALID;
+    return edge_thresholds(length, lo, up) ? MM_OK : MM_ERR_UNSUPPORTED;
 }
 
 int mm_selftest_quotient(mm_ctx *ctx, uint64_t n_pairs, uint64_t seed, uint64_t *mismatches) {

@@ -212,7 +212,11 @@ __device__ __forceinline__ void inner_step_general(const float4 &a, const float4
 }
 
 // One leaf visit (shaders.metal:127-129 with ray_rect_intersect :51-67 inlined), then pop / finish.
-template <bool CNT>
+// LITERAL = false: the two edge tests `0 <= RN(x / L) <= L` are evaluated as the equivalent interval test on x stored in
+// the record (render_kernel.cuh, RectI) — no divides by the edge lengths.  LITERAL = true (scenes with an edge length
+// outside the guarded range, or MM_FLAG_FORCE_LITERAL): the literal divides, with the lengths recomputed by the same
+// operations the upload used.
+template <bool CNT, bool LITERAL>
 __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 ori, V3 dir, float &t, uint32_t &slot, uint32_t &cur,
                                           uint32_t &head, const uint32_t *stack, Tally &tl) {
     const uint32_t first = cur & 0xFFFFFFu, count = (cur >> 24) & 0x7Fu;
@@ -221,14 +225,21 @@ __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 or
         const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
         if (CNT) tl.rect++;
         const V3 ro = mk(r0.x, r0.y, r0.z), n = mk(r1.x, r1.y, r1.z), v = mk(r2.x, r2.y, r2.z), u = mk(r3.x, r3.y, r3.z);
-        const float len_v = r0.w, len_u = r1.w;
         const float norm_check = dot3(dir, n);                                   // :53
         const float a = fdiv(dot3(sub3(ro, ori), n), norm_check);                // :55
         const V3 isect = add3(ori, scale3(dir, a));                              // :56
         const V3 rv = sub3(isect, ro);                                           // :58
-        const float d1 = fdiv(dot3(rv, v), len_v);                               // :60
-        const float d2 = fdiv(dot3(rv, u), len_u);                               // :61
-        if ((0.0f <= d1 && d1 <= len_v) && (0.0f <= d2 && d2 <= len_u) && norm_check != 0.0f && a > 0.1f && a < t) {   // :63
+        const float xv = dot3(rv, v), xu = dot3(rv, u);
+        bool inside;
+        if (LITERAL) {
+            const float len_v = length3(v), len_u = length3(u);
+            const float d1 = fdiv(xv, len_v);                                    // :60
+            const float d2 = fdiv(xu, len_u);                                    // :61
+            inside = (0.0f <= d1 && d1 <= len_v) && (0.0f <= d2 && d2 <= len_u);
+        } else {
+            inside = (r2.w <= xv) & (xv <= r0.w) & (r3.w <= xu) & (xu <= r1.w);
+        }
+        if (inside && norm_check != 0.0f && a > 0.1f && a < t) {                 // :63
             t = a;
             slot = first + i;
         }
@@ -332,7 +343,7 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
         } else {
             if (isL) {
                 if (CNT) tl.leaf++;
-                leaf_step<CNT>(rects, ori, dir, t, slot, cur, head, stack, tl);
+                leaf_step<CNT, MIXED>(rects, ori, dir, t, slot, cur, head, stack, tl);
             }
         }
     }
@@ -425,7 +436,7 @@ trace_kernel(const __grid_constant__ KParams P) {
             const bool lit = P.force_literal || !P.scene_fast_ok ||
                              !(P.rcp_mode ? (rcp_safe(ori.x, dir.x) && rcp_safe(ori.y, dir.y) && rcp_safe(ori.z, dir.z))
                                           : (axis_safe(ori.x, dir.x) && axis_safe(ori.y, dir.y) && axis_safe(ori.z, dir.z)));
-            const bool any_lit = __any_sync(0xFFFFFFFFu, alive && lit);
+            const bool any_lit = __any_sync(0xFFFFFFFFu, alive && lit) || !P.rect_fast_ok;   // MIXED also means literal rect tests
             Hit h;
             if (P.rcp_mode) {
                 if (!any_lit) h = traverse<false, CNT, true>(P.pairs, P.rects, root, alive, false, ori, dir, t, slot, &tl);
@@ -443,28 +454,35 @@ trace_kernel(const __grid_constant__ KParams P) {
                 } else {
                     nhits++;
                     const float4 *rp = reinterpret_cast<const float4 *>(P.rects + slot);
-                    const float4 r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
-                    if (DBG && n == 0) first_hit = __float_as_uint(r2.w);
+                    const float4 r1 = __ldg(rp + 1);
                     const V3 nrm = mk(r1.x, r1.y, r1.z);                   // :309 (per-rect constant, same operations)
                     const float side = -sign1(dot3(dir, nrm));             // :310
                     const float4 *sp4 = reinterpret_cast<const float4 *>(P.shade + slot);
-                    if (__float_as_uint(r3.w) == 0u || side == -1.0f) {    // :311
-                        const float4 col = __ldg(sp4), emi = __ldg(sp4 + 1);
+                    const float4 col = __ldg(sp4);                         // albedo, material bits in .w
+                    if (DBG && n == 0) first_hit = __float_as_uint(__ldg(sp4 + 1).w);
+                    if (__float_as_uint(col.w) == 0u || side == -1.0f) {   // :311
+                        const float4 emi = __ldg(sp4 + 1);
                         light = add3(light, mul3(mk(emi.x, emi.y, emi.z), color));   // :312-313
                         color = mul3(color, mk(col.x, col.y, col.z));      // :314
+                        // :315-318 rejection loop `while (length(rd) > 1)`.  RN(sqrt(s)) > 1 <=> s > 1 + 2^-23: sqrt is
+                        // monotone, sqrt(1 + 2^-23) = 1 + 2^-24 - ... lies below the midpoint and rounds to 1, and
+                        // sqrt(1 + 2^-22) rounds above 1 (checked over every float in [0.5, 2) in tests/test_oracle.py),
+                        // so the loop compares the squared length and the square root is taken once, after it.
                         V3 rd;
-                        do {                                               // :315-318
+                        float s2;
+                        do {
                             const float a = rnd_pm1(state), b = rnd_pm1(state), c = rnd_pm1(state);
                             rd = mk(a, b, c);
-                        } while (length3(rd) > 1.0f);
-                        rd = normalize3(rd);                               // :319
+                            s2 = dot3(rd, rd);
+                        } while (s2 > 1.00000011920928955f);
+                        const float rl = fsqrt(s2);                        // :319 normalize = v / length(v)
+                        rd = mk(fdiv(rd.x, rl), fdiv(rd.y, rl), fdiv(rd.z, rl));
                         ori = add3(ori, scale3(dir, t));                   // :320
                         dir = normalize3(add3(rd, scale3(nrm, side)));     // :321
                         t = 1e30f;                                         // :323
                     } else {
                         mirror_hits++;                                     // :325
                         if (mirror_hits < P.mirror_limit) {                // :326
-                            const float4 col = __ldg(sp4);
                             light = add3(light, scale3(mk(col.x, col.y, col.z), 0.005f));   // :327
                             ori = add3(ori, scale3(dir, t));               // :328
                             dir = normalize3(reflect3(dir, nrm));          // :329

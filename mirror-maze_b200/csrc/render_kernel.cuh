@@ -26,20 +26,24 @@ constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kMaxLeafCount = 126;
 
 // One rectangle in leaf order (slot s = position in the reference `indices` array), 64 B.
-// The normal and the edge lengths are per-rect constants of ray_rect_intersect (shaders.metal:52,60-61); they are
-// evaluated once at upload with the same IEEE operations the literal code performs per call, hence bit-identical.
+// The normal is a per-rect constant of ray_rect_intersect (shaders.metal:52); it is evaluated once at upload with the
+// same IEEE operations the literal code performs per call, hence bit-identical.  The edge tests of :60-63,
+//     d = RN(x / L),  0 <= d && d <= L        (x = dot(isect - origin, edge), L = length(edge), a per-rect constant)
+// are stored as an interval on x itself: lo <= x && x <= up decides exactly what the divide-then-compare decides, for
+// every x including zeros, denormals, infinities and NaN (edge_thresholds in scene_prep.cpp derives both bounds from the
+// round-to-nearest-even rule; tests/test_host_surface.py checks them against real divisions around every boundary).
 struct __align__(16) RectI {
-    float4 o_lv;   // origin.xyz, length(v)
-    float4 n_lu;   // normalize(cross(v,u)).xyz, length(u)
-    float4 v_id;   // v.xyz, bits = original plane index
-    float4 u_mat;  // u.xyz, bits = material (0 matte, 1 mirror)
+    float4 o_upv;   // origin.xyz, upper bound for dot(rv, v)
+    float4 n_upu;   // normalize(cross(v,u)).xyz, upper bound for dot(rv, u)
+    float4 v_lov;   // v.xyz, lower bound for dot(rv, v)
+    float4 u_lou;   // u.xyz, lower bound for dot(rv, u)
 };
 static_assert(sizeof(RectI) == 64, "rect is 64 B");
 
 // Shading constants per slot, 32 B: albedo and emissions.rgb * emissions.a (shaders.metal:312,314,327).
 struct __align__(16) RectS {
-    float4 color;    // rgb, unused
-    float4 emitted;  // rgb * a, unused
+    float4 color;    // rgb, bits = material (0 matte, 1 mirror)
+    float4 emitted;  // rgb * a, bits = original plane index
 };
 
 struct Counters {   // device-side mirror of mm_counters
@@ -57,6 +61,7 @@ struct KParams {
     uint32_t ppc;
     uint32_t W, H;
     uint32_t n_pairs, n_slots;
+    uint32_t rect_fast_ok;            // every edge length inside the guarded range of edge_thresholds
     uint32_t root_link, root_count;   // descriptor of node 0 (pair 0 unless the root is a leaf)
     uint32_t noise_w, noise_h;
     uint32_t force_literal;

@@ -18,6 +18,34 @@ inline bool coord_ok(float b) {
 }
 }  // namespace
 
+// The literal edge test computes d = RN(x / L) and accepts 0 <= d <= L (shaders.metal:60-63).  Both comparisons are
+// monotone in x, so each is a threshold on x; the thresholds follow from round-to-nearest-even:
+//   d <= L  <=>  x / L < m, or x / L == m and L's last mantissa bit is 0 (the tie goes to L), m = midpoint(L, next(L)).
+//       T = m * L is exact in double (25 x 24 bits).  With th = RN_f32(T) and tl = T - th: a float x satisfies x < T iff
+//       x <= th (tl > 0) or x < th (tl < 0); for tl == 0, x == T is the tie.  So `x <= up` with up = th when tl > 0 or
+//       (tl == 0 and L even), else the float below th.
+//   0 <= d  <=>  x >= 0, or x < 0 and the quotient rounds to -0: |x| / L <= 2^-150 (2^-150 is the tie between 0 and the
+//       smallest denormal and goes to 0).  With x = -k * 2^-149 that is k <= L / 2, so lo = -floor(L / 2) * 2^-149.
+// NaN x fails both forms, +-inf behaves the same in both.  L == +0 (a degenerate edge) never accepts in the literal form
+// (x / 0 is +-inf or NaN): NaN bounds reproduce that.  Guarded range otherwise: 2^-20 <= L <= 2^23 (quotients near L are
+// normal numbers, floor(L / 2) * 2^-149 is an exact denormal); anything else — denormal, huge, inf, NaN — reports false.
+bool edge_thresholds(float L, float *lo, float *up) {
+    const float nan = std::nanf("");
+    *lo = nan; *up = nan;
+    uint32_t bits;
+    std::memcpy(&bits, &L, 4);
+    if (bits == 0u) return true;                                  // +0: never accepts
+    if (!(L >= 9.5367431640625e-07f /*2^-20*/ && L <= 8388608.0f /*2^23*/)) return false;
+    const float next = std::nextafterf(L, INFINITY);
+    const double m = ((double)L + (double)next) * 0.5;            // exact
+    const double T = m * (double)L;                               // exact: 25 x 24 significant bits
+    const float th = (float)T;                                    // round to nearest even
+    const double tl = T - (double)th;                             // exact
+    *up = (tl > 0.0 || (tl == 0.0 && (bits & 1u) == 0u)) ? th : std::nextafterf(th, -INFINITY);
+    *lo = -(float)(std::floor((double)L * 0.5) * 1.401298464324817e-45 /*2^-149*/);
+    return true;
+}
+
 int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *nodes, uint32_t n_nodes,
                   const uint32_t *indices, const uint8_t *materials, const mm_float4 *emissions, Prepared &out,
                   std::string &err) {
@@ -78,6 +106,7 @@ int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *
     out.fast_ok = fast_ok;
 
     out.rects.resize(n_planes);
+    bool rect_fast_ok = true;
     out.shade.resize(n_planes);
     for (uint32_t s = 0; s < n_planes; s++) {
         const uint32_t id = indices[s];
@@ -88,15 +117,19 @@ int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *
         const float n[3] = {c[0] / lc, c[1] / lc, c[2] / lc};                                                   // normalize
         const float lv = std::sqrt(dot3(v, v)), lu = std::sqrt(dot3(u, u));
         RectI &r = out.rects[s];
-        r.o_lv = make_float4(m.origin.x, m.origin.y, m.origin.z, lv);
-        r.n_lu = make_float4(n[0], n[1], n[2], lu);
-        r.v_id = make_float4(v[0], v[1], v[2], as_float(id));
-        r.u_mat = make_float4(u[0], u[1], u[2], as_float(materials[id] ? 1u : 0u));
+        float lo_v, up_v, lo_u, up_u;
+        rect_fast_ok = edge_thresholds(lv, &lo_v, &up_v) && rect_fast_ok;
+        rect_fast_ok = edge_thresholds(lu, &lo_u, &up_u) && rect_fast_ok;
+        r.o_upv = make_float4(m.origin.x, m.origin.y, m.origin.z, up_v);
+        r.n_upu = make_float4(n[0], n[1], n[2], up_u);
+        r.v_lov = make_float4(v[0], v[1], v[2], lo_v);
+        r.u_lou = make_float4(u[0], u[1], u[2], lo_u);
         const mm_float4 &e = emissions[id];
         RectS &sh = out.shade[s];
-        sh.color = make_float4(m.color.x, m.color.y, m.color.z, 0.0f);
-        sh.emitted = make_float4(e.x * e.w, e.y * e.w, e.z * e.w, 0.0f);
+        sh.color = make_float4(m.color.x, m.color.y, m.color.z, as_float(materials[id] ? 1u : 0u));
+        sh.emitted = make_float4(e.x * e.w, e.y * e.w, e.z * e.w, as_float(id));
     }
+    out.rect_fast_ok = rect_fast_ok;
     return MM_OK;
 }
 

@@ -12,8 +12,13 @@ struct Prepared {
     std::vector<RectI> rects;
     std::vector<RectS> shade;
     uint32_t n_pairs = 0, root_link = 0, root_count = 0, depth = 0, max_leaf = 0;
-    bool fast_ok = false;
+    bool fast_ok = false;        // box coordinates inside the guarded ranges of the shared-reciprocal slab quotient
+    bool rect_fast_ok = false;   // edge lengths inside the guarded range of edge_thresholds
 };
+
+// Interval [lo, up] on x that is equivalent to `0 <= RN(x / L) && RN(x / L) <= L` (see render_kernel.cuh, RectI).
+// Returns false when L is outside the guarded range (then the kernel uses the literal divides for the whole scene).
+bool edge_thresholds(float L, float *lo, float *up);
 
 int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *nodes, uint32_t n_nodes,
                   const uint32_t *indices, const uint8_t *materials, const mm_float4 *emissions, Prepared &out,

@@ -170,6 +170,18 @@ def check_collision(nodes, bmin, bmax):
                                                      Float3(*[float(v) for v in bmax])))
 
 
+def rect_edge_thresholds(length):
+    """Interval [lo, up] on x = dot(rv, edge) equivalent to `0 <= RN(x / length) <= length` (mm_rect_edge_thresholds);
+    None when the length is outside the guarded range."""
+    import ctypes as C
+    lo, up = C.c_float(), C.c_float()
+    rc = abi.load_library().mm_rect_edge_thresholds(C.c_float(float(length)), C.byref(lo), C.byref(up))
+    if rc == -5:                      # MM_ERR_UNSUPPORTED
+        return None
+    _check(rc, "mm_rect_edge_thresholds")
+    return np.float32(lo.value), np.float32(up.value)
+
+
 class ChunkBag:
     """The progressive-refresh bag of chunk origins: gen_pixels + random_pixels (src/main.rs:293-326, 713-720, 778-784),
     with a seeded StdRng in place of the reference's non-deterministic thread_rng."""

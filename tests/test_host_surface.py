@@ -160,3 +160,48 @@ def test_check_collision(mm, scenes):
     assert mm.check_collision(sc.nodes, c - d, c + d) == -1                # the start cell is free
     wall_x = np.array([-50.0, 0.0, -45.0], dtype=F)                        # on the outer x = -50 wall
     assert mm.check_collision(sc.nodes, wall_x - d, wall_x + d) >= 0
+
+
+def _literal_edge_test(x, L):
+    """shaders.metal:60-63 for one edge: d = x / L (IEEE fp32), 0 <= d && d <= L."""
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore", under="ignore"):
+        d = (x.astype(np.float32) / np.float32(L)).astype(np.float32)
+    return (np.float32(0.0) <= d) & (d <= np.float32(L))
+
+
+def test_rect_edge_thresholds_equal_divide_then_compare(mm):
+    """The kernel's divide-free edge test: lo <= x <= up must decide exactly what 0 <= RN(x/L) <= L decides, for x at and
+    around both boundaries (several ulps each side), zeros of both signs, denormals, infinities, NaN and random x."""
+    rng = np.random.default_rng(1234)
+    lengths = [10.0, 5.0, 4.9, 0.1, 0.2, 1.0, 2.0, 3.0, 1.9999999, 2.0000002, 2.0 ** -20, 2.0 ** 23, 7.5, 1e-3, 12345.678,
+               1.0000001, 0.99999994, 16777215.0 / 4, 1e6]
+    lengths += list(np.exp(rng.uniform(np.log(2.0 ** -20), np.log(2.0 ** 23), 4000)))
+    checked = 0
+    for L in lengths:
+        L = np.float32(L)
+        th = mm.rect_edge_thresholds(L)
+        assert th is not None, L
+        lo, up = th
+        xs = [np.float32(0.0), np.float32(-0.0), np.float32(np.inf), np.float32(-np.inf), np.float32(np.nan), lo, up, L, L * L]
+        for base in (up, lo, np.float32(L * L)):
+            v = np.float32(base)
+            a = b = v
+            for _ in range(6):
+                a = np.nextafter(a, np.float32(np.inf)); b = np.nextafter(b, np.float32(-np.inf))
+                xs += [a, b]
+        den = np.float32(1.401298464324817e-45)
+        xs += [np.float32(-k) * den for k in range(0, 40)] + [np.float32(k) * den for k in range(1, 4)]
+        xs += list((rng.standard_normal(24) * float(L) * float(L)).astype(np.float32))
+        x = np.array(xs, dtype=np.float32)
+        want = _literal_edge_test(x, L)
+        got = (lo <= x) & (x <= up)
+        assert np.array_equal(want, got), (L, lo, up, x[want != got][:5])
+        checked += len(x)
+    assert checked > 300000
+    # degenerate and unguarded lengths
+    lo, up = mm.rect_edge_thresholds(0.0)
+    assert np.isnan(lo) and np.isnan(up)                       # x / 0 never passes the literal test either
+    x = np.array([0.0, -0.0, 1.0, -1.0, np.inf, np.nan], dtype=np.float32)
+    assert not _literal_edge_test(x, np.float32(0.0)).any()
+    for bad in (1e-30, 2.0 ** -21, 2.0 ** 24, np.inf, np.nan, -1.0, 1e-45):
+        assert mm.rect_edge_thresholds(bad) is None

@@ -214,3 +214,13 @@ def test_rcp_slab_variant_numpy_agrees(mm, oracle, noise, scenes, name):
         assert cnt[k] == cnt2[k], k
     same_first = (dbg["first_hit"] == lit[2]["first_hit"]).mean()
     assert same_first > 0.999          # primary hits essentially never depend on the last ulp of a slab quotient
+
+
+def test_rejection_threshold_equals_length_test():
+    """The kernel's rejection loop compares the squared length with 1 + 2^-23 instead of taking the square root
+    (shaders.metal:315-318 `while (length(rd) > 1)`).  Equivalence for every fp32 in [0.5, 2); outside, monotonicity of
+    the correctly rounded square root decides (sqrt(s) < 1 for s < 0.5, > 1 for s >= 2)."""
+    bits = np.arange(np.float32(0.5).view(np.uint32), np.float32(2.0).view(np.uint32), dtype=np.uint32)
+    s = bits.view(np.float32)
+    assert np.array_equal(np.sqrt(s) > np.float32(1.0), s > np.float32(1.00000011920928955))
+    assert np.float32(1.00000011920928955) == np.float32(1.0) + np.float32(2.0 ** -23)
