@@ -161,13 +161,12 @@ __device__ __forceinline__ void descend(float lo1, float hi1, float lo2, float h
     const bool hit2 = (hi2 >= lo2) & (lo2 < t) & (hi2 > 0.0f);
     const bool swap = hit2 & (!hit1 | (lo1 > lo2));                     // :140, ties keep the left child first
     if (!(hit1 | hit2)) {                                               // :149-150
-        cur = head == 0 ? CUR_END : stack[head - 1];
-        head = head == 0 ? 0 : head - 1;
+        cur = stack[--head];                                            // the bottom entry is the CUR_END sentinel
     } else {                                                            // :151-154
         cur = swap ? lk.y : lk.x;
         if (hit1 & hit2) {
             stack[head++] = swap ? lk.x : lk.y;
-            if (CNT) tl.max_stack = max(tl.max_stack, head);
+            if (CNT) tl.max_stack = max(tl.max_stack, head - 1u);       // entries above the sentinel
         }
     }
 }
@@ -244,8 +243,7 @@ __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 or
             slot = first + i;
         }
     }
-    cur = head == 0 ? CUR_END : stack[head - 1];
-    head = head == 0 ? 0 : head - 1;
+    cur = stack[--head];
 }
 
 // intersect_bvh_iterative (shaders.metal:115-156) for the rays of one warp.  Every lane of the warp calls this together
@@ -291,7 +289,8 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
     const char *pAB = base + (lit ? 0 : (dir.x < 0.0f ? 32 : 0) + (dir.y < 0.0f ? 64 : 0));
     const char *pZ = base + 128 + ((!lit && dir.z < 0.0f) ? 32 : 0);
     asm("" : "+l"(pAB)); asm("" : "+l"(pZ));      // keep them live: ptxas otherwise re-derives them from sign(dir) at every node
-    uint32_t cur = alive ? root : CUR_END, head = 0, slot = beam_slot;
+    stack[0] = CUR_END;                        // sentinel: popping an empty stack ends the traversal, no emptiness test
+    uint32_t cur = alive ? root : CUR_END, head = 1, slot = beam_slot;
     float t = beam_t;
     while (true) {
         const bool isI = (cur & kLeafBit) == 0u;

@@ -54,7 +54,7 @@ int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *
         err = "malformed BVH: child or leaf range out of bounds, shared child or cycle";
         return MM_ERR_BVH;
     }
-    if (depth > MM_MAX_STACK) {   // stack occupancy <= depth - 1
+    if (depth > MM_MAX_STACK) {   // stack occupancy <= depth - 1, plus the kernel's bottom sentinel
         err = "BVH depth " + std::to_string(depth) + " exceeds MM_MAX_STACK";
         return MM_ERR_BVH;
     }
