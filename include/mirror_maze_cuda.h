@@ -175,6 +175,18 @@ int mm_scatter_tiles_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params 
  * row r*max_count + k, holding group r + k*world (the interleaved partition of tile_partition / TiledFrameRenderer). */
 int mm_scatter_gathered_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, uint32_t world, uint32_t max_count,
                                const float *d_gathered, float *d_image);
+/*
+ * Render + exchange in one kernel (multi-GPU, no gather and no scatter): renders this rank's groups
+ * (params->group_first / group_step / group_count) and stores every finished pixel straight into each of the n_frames
+ * device frames given — the peer-mapped frame buffers of all ranks (NVLink peer stores), or ONE NVSwitch multicast
+ * address that replicates the store into every rank's buffer.  frames[i]: H*W*4 floats each; 1 <= n_frames <= MM_MAX_PEERS.
+ * Asynchronous on the context's stream; the caller orders a cross-rank barrier after it (the stores are complete when the
+ * kernel is).  The reference is single-GPU (main.rs:867-886 writes its one screen texture); this is the tile exchange
+ * of SURVEY section 8 (e) fused into the producing kernel.
+ */
+#define MM_MAX_PEERS 8
+int mm_render_peers_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params,
+                           float *const *frames, uint32_t n_frames);
 int mm_sync(mm_ctx *ctx);
 /* Run the context's work on a caller-owned cudaStream_t (e.g. torch's current stream) from now on; NULL
  * restores the context's own stream.  The caller keeps the stream alive while the context uses it. */

@@ -294,6 +294,23 @@ int mm_render_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params
     return do_launch(ctx, L);
 }
 
+int mm_render_peers_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, float *const *frames, uint32_t n_frames) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!frames || n_frames == 0 || n_frames > MM_MAX_PEERS) return fail(ctx, MM_ERR_INVALID, "mm_render_peers_device: 1..MM_MAX_PEERS frames");
+    for (uint32_t i = 0; i < n_frames; i++)
+        if (!frames[i]) return fail(ctx, MM_ERR_INVALID, "mm_render_peers_device: null frame pointer");
+    CK(cudaSetDevice(ctx->device));
+    Launch L;
+    int rc = build_launch(ctx, uni, params, false, L);
+    if (rc != MM_OK) return rc;
+    L.p.image = nullptr;
+    L.p.tiles = nullptr;
+    L.p.n_peers = n_frames;
+    for (uint32_t i = 0; i < n_frames; i++) L.p.peers[i] = frames[i];
+    return do_launch(ctx, L);
+}
+
 int mm_render(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, const mm_chunk *chunks, uint32_t n_chunks,
               float *out_rgba, mm_counters *counters, const mm_debug *debug) {
     if (!ctx) return MM_ERR_INVALID;

@@ -528,6 +528,10 @@ trace_kernel(const __grid_constant__ KParams P) {
         const float4 px = make_float4(fdiv(sx, d), fdiv(sy, d), fdiv(sz, d), 1.0f);
         if (P.image && pxx < P.W && pxy < P.H) reinterpret_cast<float4 *>(P.image)[(size_t)pxy * P.W + pxx] = px;
         if (P.tiles) reinterpret_cast<float4 *>(P.tiles)[(size_t)k * P.ppc + (flat >> P.log2_spp)] = px;
+        if (P.n_peers && pxx < P.W && pxy < P.H) {                      // fused exchange: NVLink peer / NVSwitch multicast stores
+            const size_t at = (size_t)pxy * P.W + pxx;
+            for (uint32_t i = 0; i < P.n_peers; i++) reinterpret_cast<float4 *>(P.peers[i])[at] = px;
+        }
     }
 
     // Event counts: warp-reduce, one atomic per warp and counter.

@@ -75,6 +75,8 @@ struct KParams {
     const uint8_t *noise;
     float *image;              // may be null
     float *tiles;              // may be null
+    float *peers[MM_MAX_PEERS];  // extra frames every finished pixel is stored into (peer-mapped or multicast), n_peers used
+    uint32_t n_peers;
     Counters *counters;
     uint32_t *dbg_first_hit, *dbg_segments, *dbg_mirror_hits;
     float *dbg_radiance;

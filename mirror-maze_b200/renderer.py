@@ -125,6 +125,11 @@ class Renderer:
     def render_device(self, uniform, params, image_ptr=None, tiles_ptr=None):
         self._ck(self._lib.mm_render_device(self._ctx, C.byref(uniform), C.byref(params), image_ptr, tiles_ptr))
 
+    def render_peers_device(self, uniform, params, frame_ptrs):
+        """mm_render_peers_device: render this rank's groups and store every pixel into each frame (peer / multicast)."""
+        arr = (C.c_void_p * len(frame_ptrs))(*[int(p) for p in frame_ptrs])
+        self._ck(self._lib.mm_render_peers_device(self._ctx, C.byref(uniform), C.byref(params), arr, len(frame_ptrs)))
+
     def scatter_tiles_device(self, uniform, params, tiles_ptr, image_ptr):
         self._ck(self._lib.mm_scatter_tiles_device(self._ctx, C.byref(uniform), C.byref(params), tiles_ptr, image_ptr))
 
@@ -169,13 +174,23 @@ class Renderer:
 
 
 class TiledFrameRenderer:
-    """One rank of the multi-GPU frame: scene replicated, groups interleaved over ranks, tiles all-gathered.
+    """One rank of the multi-GPU frame: scene replicated, groups interleaved over ranks.
 
     `dist` is torch.distributed (already initialised, backend nccl) or None for a single GPU.  Tensors are torch
-    CUDA tensors used purely as device memory; the kernels are this library's.
+    CUDA tensors used purely as device memory; the kernels are this library's.  Two ways to exchange the tiles:
+
+    exchange="peer"   the render kernel stores each finished pixel straight into every rank's frame: the frames live in
+                      torch symmetric memory, so each rank holds peer-mapped pointers to all of them (NVLink stores) and,
+                      where the fabric supports it, ONE NVSwitch multicast address that replicates a single 16-B store
+                      into all frames.  No gather, no scatter, the transfer overlaps the tracing; one barrier before (the
+                      previous frame is no longer being read anywhere) and one after (every rank's stores have landed).
+    exchange="gather" render into a compact tile buffer, NCCL all_gather_into_tensor, one scatter launch.
+    exchange="auto"   "peer" when symmetric memory can be set up for this group and world <= MM_MAX_PEERS, else "gather".
     """
 
-    def __init__(self, renderer, uniform, params, chunks, rank=0, world=1, dist=None):
+    MAX_PEERS = 8
+
+    def __init__(self, renderer, uniform, params, chunks, rank=0, world=1, dist=None, exchange="auto", multicast=True):
         import torch
 
         self.torch = torch
@@ -191,21 +206,60 @@ class TiledFrameRenderer:
         first, step, count = self.parts[rank]
         self.my = Params.from_buffer_copy(bytes(params))
         self.my.group_first, self.my.group_step, self.my.group_count = first, step, count
-        self.image = torch.zeros((self.H, self.W, 4), dtype=torch.float32, device=dev)
-        self.tiles = torch.zeros((self.max_count, self.ppc, 4), dtype=torch.float32, device=dev)
-        # concatenated all-gather layout [world * max_count, ppc, 4]; rank r's tiles are rows r*max_count ...
-        self.gathered = torch.zeros((world * self.max_count, self.ppc, 4), dtype=torch.float32, device=dev) if world > 1 else None
-        # One stream for the kernel, the collective and the scatter: a dedicated torch stream (the legacy default
-        # stream's handle is 0, which mm_set_stream reads as "use the context's own stream").
+        if exchange not in ("auto", "peer", "gather"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'gather'")
+        # One stream for the kernel, the collective / barriers and the scatter: a dedicated torch stream (the legacy
+        # default stream's handle is 0, which mm_set_stream reads as "use the context's own stream").
         self.stream = torch.cuda.Stream(dev)
+        self.exchange, self.exchange_note = "none", ""
+        self.handle, self.peer_ptrs = None, None
+        if world > 1 and exchange in ("auto", "peer"):
+            try:
+                self._setup_peer_frames(dev, multicast)
+                self.exchange = "peer"
+            except Exception as e:      # no symmetric memory on this system / group: fall back unless it was demanded
+                if exchange == "peer":
+                    raise
+                self.exchange_note = f"peer exchange unavailable ({type(e).__name__}: {e})"
+        if self.exchange != "peer":
+            self.image = torch.zeros((self.H, self.W, 4), dtype=torch.float32, device=dev)
+            if world > 1:
+                self.exchange = "gather"
+                self.tiles = torch.zeros((self.max_count, self.ppc, 4), dtype=torch.float32, device=dev)
+                # concatenated all-gather layout [world * max_count, ppc, 4]; rank r's tiles are rows r*max_count ...
+                self.gathered = torch.zeros((world * self.max_count, self.ppc, 4), dtype=torch.float32, device=dev)
         renderer.set_stream(self.stream.cuda_stream)
         renderer.set_chunks(chunks)
 
+    def _setup_peer_frames(self, dev, multicast):
+        import torch.distributed._symmetric_memory as symm
+
+        if self.world > self.MAX_PEERS:
+            raise RuntimeError(f"world {self.world} > MM_MAX_PEERS {self.MAX_PEERS}")
+        self.image = symm.empty((self.H, self.W, 4), dtype=self.torch.float32, device=dev)
+        self.image.zero_()
+        self.handle = symm.rendezvous(self.image, self.dist.group.WORLD)
+        mc = int(self.handle.multicast_ptr) if multicast else 0
+        if mc:
+            self.peer_ptrs, self.exchange_note = [mc], "NVSwitch multicast stores"
+        else:
+            self.peer_ptrs, self.exchange_note = [int(p) for p in self.handle.buffer_ptrs], "NVLink peer stores"
+        self.torch.cuda.synchronize(dev)
+        self.dist.barrier()
+
     def render_frame(self, uniform=None):
-        """Renders this rank's tiles, gathers everyone's, assembles the full frame on every rank (async)."""
+        """Renders this rank's share and assembles the full frame on every rank (asynchronous on self.stream)."""
         u = uniform if uniform is not None else self.uniform
         if self.world == 1:
             self.r.render_device(u, self.my, image_ptr=self.image.data_ptr())
+            return self.image
+        if self.exchange == "peer":
+            with self.torch.cuda.stream(self.stream):
+                self.handle.barrier(channel=0)          # every rank is done reading its previous frame
+            if self.my.group_count:
+                self.r.render_peers_device(u, self.my, self.peer_ptrs)
+            with self.torch.cuda.stream(self.stream):
+                self.handle.barrier(channel=1)          # every rank's stores have landed in this rank's frame
             return self.image
         if self.my.group_count:
             self.r.render_device(u, self.my, tiles_ptr=self.tiles.data_ptr())
