@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--mirror-limit", type=int, default=15)
     ap.add_argument("--cpu-crop", type=int, default=4, help="cpu baseline renders every k-th chunk group")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "gather"],
+                    help="N > 1: fused peer/multicast stores from the render kernel, or NCCL all-gather + scatter")
     ap.add_argument("--flags", type=int, default=0, help="MM_FLAG_* for experiments (2 = literal divides for every ray, 64 = reciprocal-multiply slab arithmetic)")
     return ap.parse_args()
 
@@ -185,7 +187,7 @@ def run_ours(a):
     p = mm.full_frame_params(u, spp=a.spp, bounce_limit=a.bounces, mirror_limit=a.mirror_limit, flags=a.flags)
     r = mm.Renderer(local)
     r.upload_scene(scene, noise)
-    frame = mm.TiledFrameRenderer(r, u, p, chunks, rank=rank, world=world, dist=dist)
+    frame = mm.TiledFrameRenderer(r, u, p, chunks, rank=rank, world=world, dist=dist, exchange=a.exchange)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)        # > 126 MB L2
 
     def barrier():
@@ -196,7 +198,8 @@ def run_ours(a):
     # exact event counts of this rank's share (deterministic; counted once with the counting kernel variant, untimed)
     pc = mm.Params.from_buffer_copy(bytes(frame.my)); pc.flags = a.flags | mm.FLAG_COUNTERS
     if pc.group_count:
-        r.render_device(u, pc, tiles_ptr=frame.tiles.data_ptr())
+        scratch = torch.zeros((frame.max_count, frame.ppc, 4), dtype=torch.float32, device=dev)
+        r.render_device(u, pc, tiles_ptr=scratch.data_ptr())
     r.sync()
     my_cnt = r.last_counters() if pc.group_count else {k: 0 for k in ("paths", "rays", "inner_visits", "leaf_visits", "rect_tests", "hits", "literal_rays", "max_stack")}
 
@@ -333,11 +336,13 @@ def run_ours(a):
                                "frac_at_load_clock": round(achieved_tops / issue_peak_now, 4),
                                "algorithmic_ops_per_launch": int(ops_per_launch),
                                "def": "50 ops per inner visit (2 slab tests x 25, a divide = 1 op) + 84 per rect test (SURVEY 8d)"}}
+    exchange_desc = (f", exchange fused into the render kernel ({frame.exchange_note})" if frame.exchange == "peer" else
+                     ", NCCL all-gather + one scatter launch" + (f" [{frame.exchange_note}]" if frame.exchange_note else ""))
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(a), "paths_per_frame": cnt_frame["paths"], "rays_per_frame": cnt_frame["rays"],
-                       "parallelism": f"image tiles x{world} (interleaved 4x4-chunk groups), scene replicated" + (", NCCL all-gather" if world > 1 else ""),
+                       "parallelism": f"image tiles x{world} (interleaved 4x4-chunk groups), scene replicated" + (exchange_desc if world > 1 else ""),
                        "l2_flush": "256 MiB device fill between timed iterations", "nodes_in_shared": info["nodes_in_shared"],
                        "blocks_per_sm": info["blocks_per_sm"], "bvh_nodes": info["n_nodes"], "planes": info["n_planes"],
                        "literal_rays_per_frame": cnt_frame["literal_rays"],
@@ -346,8 +351,10 @@ def run_ours(a):
             "e2e": {"value": round(e2e_rays / e2e_s / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": round(1e3 * e2e_s / e2e_steps, 4), "steps": e2e_steps,
                     "api": "mm_render (host chunk list + uniform in, host frame out)" if world == 1 else
-                           "mm_set_chunks + mm_render_device + NCCL all-gather + mm_scatter_gathered_device + frame to pinned host on rank 0"},
-            "gpu_launches": a.steps * (1 if world == 1 else 2), "counters": cnt_frame}
+                           ("mm_set_chunks + mm_render_peers_device (pixels stored into every rank's frame) + barrier + frame to pinned host on rank 0"
+                            if frame.exchange == "peer" else
+                            "mm_set_chunks + mm_render_device + NCCL all-gather + mm_scatter_gathered_device + frame to pinned host on rank 0")},
+            "gpu_launches": a.steps * (2 if frame.exchange == "gather" else 1), "counters": cnt_frame}
     if not a.no_cpu_baseline and world == 1:
         val, cinfo = cpu_reference_run(a, 1, 0)
         line["cpu_baseline"] = {"value": round(val, 3), "unit": UNIT, "cores": cinfo["cores"], "kind": "port", "sample": cinfo["sample"]}
