@@ -253,12 +253,6 @@ __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 or
 // reference's sequence of visits for its own ray; only the interleaving between lanes changes.  (A plain while-while
 // loop — all lanes descend to a leaf, then all test — left 12 of 32 lanes active in the interior body; see profiles/.)
 // `lit` lanes (operands outside the guarded ranges, or MM_FLAG_FORCE_LITERAL) use the general slab form.
-#ifndef MM_LD256
-#define MM_LD256 1
-#endif
-#ifndef MM_UNROLL_REPS
-#define MM_UNROLL_REPS 0
-#endif
 #ifndef MM_LEAF_WEIGHT
 #define MM_LEAF_WEIGHT 4
 #endif
@@ -298,34 +292,19 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
         const unsigned mI = __ballot_sync(0xFFFFFFFFu, isI), mL = __ballot_sync(0xFFFFFFFFu, isL);
         if ((mI | mL) == 0u) break;
         if (mI != 0u && __popc(mI) >= kLeafWeight * __popc(mL)) {
-#if MM_UNROLL_REPS
-#pragma unroll
-#else
 #pragma unroll 1
-#endif
             for (uint32_t rep = 0; rep < kInnerReps; rep++) {
                 if ((cur & kLeafBit) == 0u) {
                     const size_t off = cur;                      // interior descriptors are byte offsets
                     if (CNT) tl.inner++;
                     if (!MIXED || !lit) {
-#if MM_LD256 == 2
-                        const Line32 ab = ldg256(pAB + off), zl = ldg256(pZ + off);
-                        ulonglong2 A, B, Z;
-                        A.x = ab.x; A.y = ab.y; B.x = ab.z; B.y = ab.w; Z.x = zl.x; Z.y = zl.y;
-                        uint2 lk;
-                        asm("mov.b64 {%0, %1}, %2;" : "=r"(lk.x), "=r"(lk.y) : "l"(zl.z));
-#elif MM_LD256 == 1
+                        // 32-B load for (A, B): measured 1.5 % faster than two 16-B loads; folding (Z, link) into a second
+                        // 32-B load gave nothing (profiles/r1_block_shape.txt)
                         const Line32 ab = ldg256(pAB + off);
                         ulonglong2 A, B;
                         A.x = ab.x; A.y = ab.y; B.x = ab.z; B.y = ab.w;
                         const ulonglong2 Z = __ldg(reinterpret_cast<const ulonglong2 *>(pZ + off));
                         const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(pZ + off + 16));
-#else
-                        const ulonglong2 A = __ldg(reinterpret_cast<const ulonglong2 *>(pAB + off));
-                        const ulonglong2 B = __ldg(reinterpret_cast<const ulonglong2 *>(pAB + off + 16));
-                        const ulonglong2 Z = __ldg(reinterpret_cast<const ulonglong2 *>(pZ + off));
-                        const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(pZ + off + 16));
-#endif
                         inner_step_packed<CNT, RCP>(A, B, Z, lk, k, t, cur, head, stack, tl);
                     } else {
                         const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(base + 144 + off));

@@ -134,6 +134,66 @@ def test_device_tiles_gather_and_scatter(mm, noise, scenes, renderer):
     r2.close()
 
 
+def test_fused_exchange_stores_every_pixel_into_every_frame(mm, noise, scenes, renderer):
+    """mm_render_peers_device, as the multi-GPU peer/multicast exchange uses it (ranks emulated on one GPU, the 'peer'
+    frames are plain local buffers): after every rank's launch, each frame holds the whole single-call frame."""
+    import torch
+
+    sc, u, p, ch = build_case(mm, "yaw", scenes)
+    renderer.upload_scene(sc, noise)
+    full = renderer.render(u, p, ch)[0]
+    dev = torch.device("cuda", 0)
+    r2 = mm.Renderer(0)
+    r2.upload_scene(sc, noise)
+    r2.set_chunks(ch)
+    world = 3
+    frames = [torch.zeros((int(u.view_height), int(u.view_width), 4), dtype=torch.float32, device=dev) for _ in range(world)]
+    for rank in range(world):
+        q = mm.Params.from_buffer_copy(bytes(p))
+        q.group_first, q.group_step, q.group_count = mm.tile_partition(p.grid_x * p.grid_y, rank, world)
+        r2.render_peers_device(u, q, [f.data_ptr() for f in frames])
+    r2.sync()
+    torch.cuda.synchronize()
+    for f in frames:
+        assert f.cpu().numpy().tobytes() == full.tobytes()
+    with pytest.raises(mm.MMError):
+        r2.render_peers_device(u, p, [])
+    with pytest.raises(mm.MMError):
+        r2.render_peers_device(u, p, [frames[0].data_ptr()] * 9)
+    r2.close()
+
+
+def test_device_tiles_gather_and_scatter(mm, noise, scenes, renderer):
+    """mm_render_device -> tiles, then mm_scatter_tiles_device, as the NCCL path uses them (world emulated on one GPU)."""
+    import torch
+
+    sc, u, p, ch = build_case(mm, "yaw", scenes)
+    renderer.upload_scene(sc, noise)
+    full = renderer.render(u, p, ch)[0]
+    dev = torch.device("cuda", 0)
+    r2 = mm.Renderer(0)
+    r2.upload_scene(sc, noise)
+    r2.set_chunks(ch)
+    world = 4
+    parts = [mm.tile_partition(p.grid_x * p.grid_y, r, world) for r in range(world)]
+    ppc = u.chunk_width ** 2
+    max_count = max(pt[2] for pt in parts)
+    gathered = torch.zeros((world, max_count, ppc, 4), dtype=torch.float32, device=dev)
+    for rank in range(world):
+        q = mm.Params.from_buffer_copy(bytes(p))
+        q.group_first, q.group_step, q.group_count = parts[rank]
+        r2.render_device(u, q, tiles_ptr=gathered[rank].data_ptr())
+    image = torch.zeros((int(u.view_height), int(u.view_width), 4), dtype=torch.float32, device=dev)
+    for rank in range(world):
+        q = mm.Params.from_buffer_copy(bytes(p))
+        q.group_first, q.group_step, q.group_count = parts[rank]
+        r2.scatter_tiles_device(u, q, gathered[rank].data_ptr(), image.data_ptr())
+    r2.sync()
+    torch.cuda.synchronize()
+    assert image.cpu().numpy().tobytes() == full.tobytes()
+    r2.close()
+
+
 def test_persistent_screen_texture_semantics(mm, noise, scenes):
     """Like the reference's private screen texture (main.rs:702-709), pixels of chunks that a dispatch does not render
     keep the value of the previous dispatch (progressive refresh, main.rs:778-784)."""
