@@ -343,7 +343,7 @@ def run_ours(a):
             "data": "synthetic",
             "config": {"workload": workload_name(a), "paths_per_frame": cnt_frame["paths"], "rays_per_frame": cnt_frame["rays"],
                        "parallelism": f"image tiles x{world} (interleaved 4x4-chunk groups), scene replicated" + (exchange_desc if world > 1 else ""),
-                       "l2_flush": "256 MiB device fill between timed iterations", "nodes_in_shared": info["nodes_in_shared"],
+                       "l2_flush": "256 MiB device fill between timed iterations", "fast_slab_ok": info["fast_slab_ok"], "fast_rect_ok": info["fast_rect_ok"],
                        "blocks_per_sm": info["blocks_per_sm"], "bvh_nodes": info["n_nodes"], "planes": info["n_planes"],
                        "literal_rays_per_frame": cnt_frame["literal_rays"],
                        "arithmetic": "opt-in (b-o)*RN(1/d) slab quotients (MM_FLAG_RCP_SLAB)" if (a.flags & 64) else "IEEE fp32, slab quotients bit-identical to the literal (b-o)/d"},

@@ -200,7 +200,7 @@ int mm_stream(mm_ctx *ctx, void **stream);
 /* Static facts of the loaded scene / selected kernel (for reports). */
 typedef struct mm_scene_info {
     uint32_t n_planes, n_nodes, bvh_depth, max_leaf;
-    uint32_t nodes_in_shared;   /* always 0: child pairs are read through L1 (kept for layout stability) */
+    uint32_t fast_rect_ok;      /* 1 when every edge length allows the divide-free rect edge test      */
     uint32_t fast_slab_ok;      /* 1 when scene bounds allow the shared-reciprocal exact slab test    */
     uint32_t smem_bytes, block_threads, blocks_per_sm, n_sms;
 } mm_scene_info;

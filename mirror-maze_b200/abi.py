@@ -79,7 +79,7 @@ class Debug(C.Structure):
 
 
 class SceneInfo(C.Structure):
-    _fields_ = [(n, C.c_uint32) for n in ("n_planes", "n_nodes", "bvh_depth", "max_leaf", "nodes_in_shared", "fast_slab_ok",
+    _fields_ = [(n, C.c_uint32) for n in ("n_planes", "n_nodes", "bvh_depth", "max_leaf", "fast_rect_ok", "fast_slab_ok",
                                           "smem_bytes", "block_threads", "blocks_per_sm", "n_sms")]
 
     def as_dict(self):

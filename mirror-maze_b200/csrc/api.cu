@@ -506,7 +506,7 @@ int mm_get_scene_info(mm_ctx *ctx, mm_scene_info *out) {
     if (!ctx || !out) return MM_ERR_INVALID;
     if (!ctx->have_scene) return fail(ctx, MM_ERR_NO_SCENE, "no scene uploaded");
     out->n_planes = ctx->n_slots; out->n_nodes = ctx->n_nodes; out->bvh_depth = ctx->depth; out->max_leaf = ctx->max_leaf;
-    out->nodes_in_shared = 0u;   // child pairs are read through L1 (a shared-memory copy measured slower, profiles/r1_sched_sweep.txt)
+    out->fast_rect_ok = ctx->rect_fast_ok ? 1u : 0u;
     out->fast_slab_ok = ctx->fast_ok ? 1u : 0u;
     out->smem_bytes = ctx->last_smem; out->block_threads = ctx->last_block_threads; out->blocks_per_sm = ctx->last_blocks_per_sm;
     out->n_sms = (uint32_t)ctx->n_sms;

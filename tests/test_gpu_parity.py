@@ -362,6 +362,37 @@ def test_literal_lanes_inside_fast_warps(mm, oracle, noise, scenes, renderer):
     assert_same((img, cnt, dbg), oracle.render(sc, noise, u, p, ch, debug=True))
 
 
+def test_unguarded_edge_lengths_take_the_literal_rect_test(mm, oracle, noise, scenes):
+    """A scene with an edge longer than 2^23 and one shorter than 2^-20 is outside the guarded range of the divide-free
+    edge test: the upload reports fast_rect_ok = 0 and the kernel runs the literal divides — still bit-identical."""
+    import types
+    from mirror_maze_b200.host import PLANE_DTYPE, build_bvh
+
+    base = scenes(10)
+    extra = np.zeros(2, dtype=PLANE_DTYPE)
+    extra[0] = ((-8.5e6, 1.9, -8.5e6), (1.7e7, 0.0, 0.0), (0.0, 0.0, 1.7e7), (0.5, 0.5, 0.5))       # giant floor just above the floor
+    extra[1] = ((-5.0, 0.0, -40.0), (5e-7, 0.0, 0.0), (0.0, -3.0, 0.0), (0.9, 0.1, 0.1))            # sliver in front of the camera
+    planes = np.concatenate([base.planes, extra])
+    nodes, indices = build_bvh(planes)
+    sc = types.SimpleNamespace(planes=planes, nodes=nodes, indices=indices,
+                               materials=np.concatenate([base.materials, np.zeros(2, np.uint8)]),
+                               emissions=np.concatenate([base.emissions, np.zeros((2, 4), np.float32)]))
+    u = mm.default_uniform(10, 64, 32, 4)
+    ch = mm.gen_chunks(64, 32, 4)
+    p = mm.full_frame_params(u, spp=8, bounce_limit=5)
+    r = mm.Renderer(0)
+    r.upload_scene(sc, noise)
+    assert r.scene_info()["fast_rect_ok"] == 0 and r.scene_info()["fast_slab_ok"] == 1
+    got = r.render(u, p, ch, debug=True)
+    assert (got[2]["first_hit"] == len(planes) - 2).any()     # the giant floor is what primary rays see below the horizon
+    assert_same(got, oracle.render(sc, noise, u, p, ch, debug=True))
+    r.close()
+    r = mm.Renderer(0)
+    r.upload_scene(base, noise)
+    assert r.scene_info()["fast_rect_ok"] == 1
+    r.close()
+
+
 def test_full_size_frame_equals_oracle(mm, noise, scenes, renderer):
     """BASELINE configs[1] at FULL size — 32x32 maze, 1920x1080, 16 spp, 8 bounces, 33.2 M paths, 268 M rays — the whole
     frame and every counter against the CPU oracle (about 10-20 s of host time on the GPU box's cores)."""
