@@ -9,11 +9,16 @@
 //   intersect_bvh_iterative                              :115-156
 //   compute_shader (mapping, ray-gen, seed, bounce loop, tone-map, reduction, store)   :245-368
 //
-// PARITY UNPINNED BY THE REFERENCE: the reference has no tests, golden vectors or fixtures for this path
-// (SURVEY §4, §8 c), its device code only runs on Apple GPUs and was compiled with fast-math + FTZ, so there is no
-// reference output to compare with.  What pins this file instead: the hand-derived known-answer vectors of
-// SURVEY Appendix E (seed + random()), an independent numpy-float32 transcription (oracle/np_oracle.py) that
-// tests/ compare with this one path by path, and the committed fixtures under tests/golden/.
+// PARITY PIN: the reference has no tests, golden vectors or fixtures for this path (SURVEY §4, §8 c) and its binary only
+// runs on Apple GPUs (fast-math + FTZ AIR).  But its device SOURCE is a C++ dialect: oracle/ref_shader/ compiles reference
+// src/shaders.metal, unmodified, with g++ (msl_shim.h stands in for <metal_stdlib>) into oracle/_ref/libref_shader.so and
+// runs the reference's own compute_shader on the CPU.  tests/test_ref_shader.py pins this file to it — random(),
+// intersect_aabb, ray_rect_intersect, quat_mult on random and edge inputs, and whole dispatches image for image (every
+// shape the unmodified shader can address: its literal limits 5 / 15, spp 8..256, chunk 1..8); the digests of its images
+// are committed under tests/golden/.  What the reference cannot pin stays this file's decision, shared with the shim: the
+// arithmetic of Metal's library functions (below) and everything the shader hard-wires (other limits, spp < 8, full
+// frames) — for those: the known-answer vectors of SURVEY Appendix E, the independent numpy-float32 transcription
+// (oracle/np_oracle.py) compared path by path, and the committed fixtures.
 //
 // Canonical arithmetic — the kernel under test obeys the same rules:
 //   fp32 only; every + - * / sqrt is one IEEE-754 round-to-nearest-even operation (build with

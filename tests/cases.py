@@ -41,7 +41,20 @@ CASES = {
     "on_plane": dict(maze=16, W=64, H=32, chunk=4, spp=8, bounce=5, mirror=15, center=(0.0, 0.0, -75.0), half_theta=0.3),
     # ragged: frame not a multiple of the chunk => gen_chunks floors (main.rs:294-295) and border pixels stay unwritten
     "ragged": dict(maze=10, W=50, H=30, chunk=4, spp=8, bounce=3, mirror=15),
+    # Dispatches the reference's UNMODIFIED shader can address (oracle/ref_shader.py): its literal limits 5 / 15, at least
+    # 8 samples, at most 1024 threads per group and grid_x == (W / 2) / chunk^2 (shaders.metal:266,294-295,343-358).
+    # ref_dispatch above is the reference's own 1024 x 768 dispatch; these vary maze, pose, chunk, spp and time.
+    "refsh_maze16_yaw": dict(maze=16, W=256, H=128, chunk=4, spp=16, bounce=5, mirror=15, time=9, half_theta=0.7,
+                             grid=(8, 6), bag_seed=5),
+    "refsh_chunk2_spp64": dict(maze=10, W=128, H=64, chunk=2, spp=64, bounce=5, mirror=15, time=1, grid=(16, 10), bag_seed=6),
+    "refsh_chunk8_spp16": dict(maze=32, W=512, H=256, chunk=8, spp=16, bounce=5, mirror=15, time=2, half_theta=2.2,
+                               center=(15.0, 0.0, 25.0), grid=(4, 5), bag_seed=7),
+    "refsh_chunk1_spp256": dict(maze=10, W=64, H=64, chunk=1, spp=256, bounce=5, mirror=15, time=77, grid=(32, 8), bag_seed=8),
+    "refsh_spp8": dict(maze=10, W=256, H=64, chunk=4, spp=8, bounce=5, mirror=15, time=4, half_theta=1.3, grid=(8, 4), bag_seed=9),
 }
+
+# cases the compiled reference shader can run (the fixtures hold its image digests, see tests/golden/make_golden.py)
+REF_SHADER_CASES = ["ref_dispatch", "refsh_maze16_yaw", "refsh_chunk2_spp64", "refsh_chunk8_spp16", "refsh_chunk1_spp256", "refsh_spp8"]
 
 # cases small enough for the numpy transcription
 NP_CASES = ["cfg1", "yaw", "tiny_origin", "on_plane", "chunk1_spp256", "chunk5_spp32", "chunk16_spp1", "chunk2_spp4", "chunk8_spp2", "chunk3_spp32", "mirror_limit2", "bounce0", "bounce1", "all_miss", "ragged"]

@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import CASES, build_case
+from cases import CASES, REF_SHADER_CASES, build_case
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
@@ -360,6 +360,21 @@ def test_literal_lanes_inside_fast_warps(mm, oracle, noise, scenes, renderer):
     assert cnt["literal_rays"] >= cnt["paths"]            # at least the primary segment of every path
     assert cnt["literal_rays"] < cnt["rays"]              # later segments are back on the fast path
     assert_same((img, cnt, dbg), oracle.render(sc, noise, u, p, ch, debug=True))
+
+
+@pytest.mark.parametrize("name", REF_SHADER_CASES)
+def test_cuda_image_equals_reference_shader_image(mm, noise, scenes, renderer, name):
+    """The CUDA kernel against the reference's OWN shader source (compiled as C++ in the authoring container,
+    oracle/_ref/libref_shader.so, see oracle/ref_shader/): the fp32 image of every dispatch shape the unmodified shader
+    can address, bit for bit — directly when the library travelled to this box, and through its committed digest."""
+    from oracle import ref_shader
+
+    sc, u, p, ch = build_case(mm, name, scenes)
+    renderer.upload_scene(sc, noise)
+    img, cnt, _ = renderer.render(u, p, ch)
+    assert hashlib.sha256(img.tobytes()).hexdigest() == GOLDEN[name]["ref_shader_image"]
+    if ref_shader.available():
+        assert img.tobytes() == ref_shader.render(sc, noise, u, p, ch).tobytes()
 
 
 def test_unguarded_edge_lengths_take_the_literal_rect_test(mm, oracle, noise, scenes):
