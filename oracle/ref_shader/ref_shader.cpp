@@ -206,6 +206,26 @@ void ref_quat_mult(const float *vec3, const float *quat4, float *out3) {        
     out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
 }
 
+// The reference's fragment_shader (shaders.metal:214-225) evaluated for every pixel of an image, each against the
+// UNBLURRED image (the shader blurs in place, which makes a pass order-dependent; the product defines the pass as
+// ping-pong).  The pixel's own texel is restored after each call; dst receives the returned colour.
+void ref_fragment_blur(const float *src, uint32_t W, uint32_t H, float *dst) {
+    std::vector<float> scratch(src, src + (size_t)W * H * 4);
+    metal::texture2d<float, metal::access::read_write> image;
+    image.rgba = scratch.data(); image.width = W; image.height = H;
+    for (uint32_t y = 0; y < H; y++)
+        for (uint32_t x = 0; x < W; x++) {
+            ColorInOut in;
+            in.position = metal::float4((float)x + 0.5f, (float)y + 0.5f, 0.0f, 1.0f);      // [[position]]: pixel centres
+            float *texel = scratch.data() + 4 * ((size_t)y * W + x);
+            const float keep[4] = {texel[0], texel[1], texel[2], texel[3]};
+            const metal::float4 c = fragment_shader(in, image);
+            std::memcpy(texel, keep, sizeof(keep));
+            float *o = dst + 4 * ((size_t)y * W + x);
+            o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w;
+        }
+}
+
 int ref_shader_limits(int *bounce_limit, int *mirror_limit) {   // the literals of shaders.metal:294-295, for the tests' parameters
     *bounce_limit = 5; *mirror_limit = 15;
     return 0;

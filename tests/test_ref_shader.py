@@ -154,6 +154,21 @@ def test_oracle_image_equals_committed_reference_shader_digest(oracle, mm, noise
     assert hashlib.sha256(got.tobytes()).hexdigest() == GOLDEN[name]["ref_shader_image"]
 
 
+def test_present_blur_matches_reference_fragment_shader(ref):
+    """fragment_shader (shaders.metal:214-225), per pixel against the unblurred image, vs the ping-pong blur model that
+    the CUDA present pass is tested against."""
+    from oracle import np_oracle
+    L = ref.lib()
+    L.ref_fragment_blur.restype = None
+    L.ref_fragment_blur.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    rng = np.random.default_rng(21)
+    for (H, W) in ((1, 1), (2, 3), (5, 7), (33, 65), (120, 160)):
+        img = rng.random((H, W, 4), dtype=np.float32)
+        out = np.zeros_like(img)
+        L.ref_fragment_blur(img.ctypes.data, W, H, out.ctypes.data)
+        assert out.tobytes() == np_oracle.present_blur(img).tobytes()
+
+
 def test_seed_saturation_happens_in_these_cases(oracle):
     """The float -> uint conversion of the seed (shaders.metal:298) saturates for threads whose fp32 sum reaches 2^32;
     C++ leaves that cast undefined and x86 would wrap, so the shim's saturating conversion is exercised, not assumed."""
