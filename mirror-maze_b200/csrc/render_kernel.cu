@@ -46,14 +46,16 @@ __device__ __forceinline__ V3 normalize3(V3 a) { float l = length3(a); return mk
 __device__ __forceinline__ V3 reflect3(V3 i, V3 n) { return sub3(i, scale3(n, fmul(2.0f, dot3(n, i)))); }
 __device__ __forceinline__ float sign1(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 
-// shaders.metal:181-186
-__device__ __forceinline__ float random_f(uint32_t &state) {
+// random() of shaders.metal:181-186 (state = state * 747796405 + 291336453; PCG output hash; float(result) / 2^32) is only
+// ever used as (random(state) - 0.5) * 2.0 (:303, :315-317), evaluated here as one FMA: float(r) * 2^-32 is an exact scaling, and so is the
+// final * 2, hence 2 * RN(f * 2^-32 - 0.5) == RN(f * 2^-31 - 1), which is what the FMA's single rounding returns
+// (tests/test_oracle.py checks the identity over 2^24 random words and the edge words).
+__device__ __forceinline__ float rnd_pm1(uint32_t &state) {
     state = state * 747796405u + 291336453u;
     uint32_t result = ((state >> ((state >> 28) + 4u)) ^ state) * 277803737u;
     result = (result >> 22) ^ result;
-    return fmul(__uint2float_rn(result), 2.3283064365386963e-10f);   // float(result) / 2^32, exact scaling
+    return __fmaf_rn(__uint2float_rn(result), 4.656612873077393e-10f /*2^-31*/, -1.0f);
 }
-__device__ __forceinline__ float rnd_pm1(uint32_t &state) { return fmul(fsub(random_f(state), 0.5f), 2.0f); }
 
 // shaders.metal:163-172
 struct Q4 { float x, y, z, w; };

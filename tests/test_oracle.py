@@ -224,3 +224,15 @@ def test_rejection_threshold_equals_length_test():
     s = bits.view(np.float32)
     assert np.array_equal(np.sqrt(s) > np.float32(1.0), s > np.float32(1.00000011920928955))
     assert np.float32(1.00000011920928955) == np.float32(1.0) + np.float32(2.0 ** -23)
+
+
+def test_fused_random_direction_component_is_bit_identical():
+    """The kernel evaluates (random(state) - 0.5) * 2.0 as fma(float(r), 2^-31, -1): both scalings are exact, so the
+    single rounding of the FMA equals the rounding of the subtraction."""
+    rng = np.random.default_rng(0)
+    r = np.concatenate([rng.integers(0, 2 ** 32, 1 << 24, dtype=np.uint64),
+                        np.array([0, 1, 2, 2 ** 31 - 1, 2 ** 31, 2 ** 31 + 1, 2 ** 32 - 1, 2 ** 32 - 128, 2 ** 24, 2 ** 24 + 1, 2 ** 25 + 1], dtype=np.uint64)]).astype(np.uint32)
+    f = r.astype(np.float32)
+    literal = ((f * np.float32(2.0 ** -32)) - np.float32(0.5)) * np.float32(2.0)
+    fused = (f.astype(np.float64) * 2.0 ** -31 - 1.0).astype(np.float32)        # the exact value, rounded once
+    assert np.array_equal(literal.view(np.uint32), fused.view(np.uint32))
