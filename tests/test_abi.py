@@ -99,3 +99,19 @@ def test_headless_driver_fails_loudly_without_gpu(mm):
     exe = os.path.join(os.path.dirname(mm.library_path()), "mm_headless")
     out = subprocess.run([exe, "--maze", "4", "--width", "16", "--height", "16", "--spp", "1"], capture_output=True, text=True, timeout=120)
     assert out.returncode != 0 and "mm_create failed" in out.stderr
+
+
+def test_packed_fp32_instruction_mix_shows_no_contraction():
+    """ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 regardless of the rounding modifiers (docs/exact_quotient.md),
+    which would round once where the contract rounds twice.  The slab sequence is add, mul, fma, fma, fma per quotient pair
+    (add, mul in the reciprocal-multiply mode), six pairs per visit: over all instantiations the SASS must hold exactly
+    FADD2 : FMUL2 : FFMA2 = 2 : 2 : 3.  A fused or dropped instruction changes the ratio."""
+    import shutil
+    import subprocess
+    obj = os.path.join(ROOT, "mirror-maze_b200", "build", "render_kernel.o")
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not (os.path.exists(obj) and os.path.exists(tool)):
+        pytest.skip("needs the built render_kernel.o and cuobjdump")
+    sass = subprocess.run([tool, "-sass", obj], capture_output=True, text=True, check=True).stdout
+    n_add, n_mul, n_fma = (sass.count(f" {op} ") for op in ("FADD2", "FMUL2", "FFMA2"))
+    assert n_add > 0 and n_add == n_mul and 2 * n_fma == 3 * n_mul, (n_add, n_mul, n_fma)
