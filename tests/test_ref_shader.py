@@ -182,3 +182,33 @@ def test_seed_saturation_happens_in_these_cases(oracle):
                 sat += 1
                 assert O.mmo_seed(C.c_float(float(n)), C.c_float(float(n)), tx, ty, 0) == 0xFFFFFFFF
     assert sat > 0
+
+
+def test_random_dispatches_equal_reference_shader(ref, oracle, mm, noise):
+    """Seeded random mazes, poses, times, chunk subsets and dispatch shapes (chunk 2/4/8, spp 8..64) among those the
+    unmodified shader can address: oracle image vs reference-shader image, bit for bit."""
+    rng = np.random.default_rng(77)
+    done = 0
+    for _ in range(16):
+        maze = int(rng.choice([10, 16, 32]))
+        chunk = int(rng.choice([2, 4, 8]))
+        spp = int(rng.choice([s for s in (8, 16, 32, 64) if chunk * chunk * s <= 1024]))
+        gx, gy = int(rng.choice([2, 4, 8])), int(rng.integers(1, 7))
+        W, H = 2 * chunk * chunk * gx, int(rng.choice([32, 64, 96]))
+        sc = mm.MazeScene(maze, 0)
+        half = 5.0 * maze
+        cell = rng.integers(0, maze, size=2)
+        center = (-half + 10.0 * cell[0] + float(rng.uniform(0.5, 9.5)), float(rng.uniform(-7.5, 1.9)),
+                  -half + 10.0 * cell[1] + float(rng.uniform(0.5, 9.5)))
+        u = mm.default_uniform(maze, W, H, chunk, time=int(rng.integers(0, 100000)), camera_center=center,
+                               half_theta=float(rng.uniform(0.0, np.pi)))
+        allc = mm.gen_chunks(W, H, chunk)
+        ch = allc[rng.permutation(len(allc))[: gx * gy]].copy()
+        if len(ch) < gx * gy:
+            continue
+        p = mm.full_frame_params(u, spp=spp, bounce_limit=5, mirror_limit=15)
+        p.grid_x, p.grid_y = gx, gy
+        got, _, _ = oracle.render(sc, noise, u, p, ch)
+        assert got.tobytes() == ref.render(sc, noise, u, p, ch).tobytes(), (maze, chunk, spp, gx, gy, center)
+        done += 1
+    assert done >= 10

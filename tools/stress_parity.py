@@ -33,7 +33,48 @@ def main():
             if not ok:
                 print("MISMATCH maze", maze, "pose", i, center)
     print(f"stress parity: {n_poses} poses over mazes 10/32/64/128, {rays} rays ({lit} on the literal-divide path), mismatches: {bad}, {time.time() - t0:.1f} s")
+    bad += against_reference_shader(r, noise, max(8, n_poses // 5))
     return 1 if bad else 0
+
+
+def against_reference_shader(r, noise, n_poses):
+    """The same idea against the reference's own shader compiled as C++ (oracle/_ref, when the library travelled here):
+    random poses, times and chunk subsets in dispatch shapes the unmodified shader can address (limits 5 / 15,
+    grid_x = (W / 2) / chunk^2, spp 8..64) — GPU image vs reference-shader image, bit for bit."""
+    from oracle import ref_shader
+    if not ref_shader.available():
+        print("reference-shader stress: oracle/_ref/libref_shader.so not present, skipped")
+        return 0
+    rng = np.random.default_rng(77)
+    bad, t0, px = 0, time.time(), 0
+    for i in range(n_poses):
+        maze = int(rng.choice([10, 16, 32]))
+        chunk = int(rng.choice([2, 4, 8]))
+        spp = int(rng.choice([s for s in (8, 16, 32, 64) if chunk * chunk * s <= 1024]))
+        gx = int(rng.choice([2, 4, 8])); gy = int(rng.integers(1, 7))
+        W = 2 * chunk * chunk * gx; H = int(rng.choice([32, 64, 96]))
+        sc = mm.MazeScene(maze, 0)
+        r.upload_scene(sc, noise)
+        half = 5.0 * maze
+        cell = rng.integers(0, maze, size=2)
+        center = (-half + 10.0 * cell[0] + float(rng.uniform(0.5, 9.5)), float(rng.uniform(-7.5, 1.9)), -half + 10.0 * cell[1] + float(rng.uniform(0.5, 9.5)))
+        u = mm.default_uniform(maze, W, H, chunk, time=int(rng.integers(0, 100000)), camera_center=center, half_theta=float(rng.uniform(0.0, np.pi)))
+        allc = mm.gen_chunks(W, H, chunk)
+        ch = allc[rng.permutation(len(allc))[: gx * gy]].copy()
+        if len(ch) < gx * gy:
+            continue
+        p = mm.full_frame_params(u, spp=spp, bounce_limit=5, mirror_limit=15)
+        p.grid_x, p.grid_y = gx, gy
+        img, cnt, _ = r.render(u, p, ch)
+        ref = ref_shader.render(sc, noise, u, p, ch)
+        ok = img.tobytes() == ref.tobytes()
+        bad += 0 if ok else 1
+        px += int((ref[..., 3] == 1).sum())
+        if not ok:
+            print("REFERENCE-SHADER MISMATCH pose", i, maze, chunk, spp, gx, gy, center)
+    print(f"reference-shader stress: {n_poses} random dispatches (mazes 10/16/32, chunk 2/4/8, spp 8..64), {px} pixels, "
+          f"GPU vs the reference's own shader: mismatches: {bad}, {time.time() - t0:.1f} s")
+    return bad
 
 if __name__ == "__main__":
     sys.exit(main())
