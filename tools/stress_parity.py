@@ -33,11 +33,12 @@ def main():
             if not ok:
                 print("MISMATCH maze", maze, "pose", i, center)
     print(f"stress parity: {n_poses} poses over mazes 10/32/64/128, {rays} rays ({lit} on the literal-divide path), mismatches: {bad}, {time.time() - t0:.1f} s")
-    bad += against_reference_shader(r, noise, max(8, n_poses // 5))
+    r.close()
+    bad += against_reference_shader(noise, max(8, n_poses // 5))
     return 1 if bad else 0
 
 
-def against_reference_shader(r, noise, n_poses):
+def against_reference_shader(noise, n_poses):
     """The same idea against the reference's own shader compiled as C++ (oracle/_ref, when the library travelled here):
     random poses, times and chunk subsets in dispatch shapes the unmodified shader can address (limits 5 / 15,
     grid_x = (W / 2) / chunk^2, spp 8..64) — GPU image vs reference-shader image, bit for bit."""
@@ -54,7 +55,8 @@ def against_reference_shader(r, noise, n_poses):
         gx = int(rng.choice([2, 4, 8])); gy = int(rng.integers(1, 7))
         W = 2 * chunk * chunk * gx; H = int(rng.choice([32, 64, 96]))
         sc = mm.MazeScene(maze, 0)
-        r.upload_scene(sc, noise)
+        r = mm.Renderer(0)                  # fresh zero-filled screen: the dispatch renders a subset of the chunks and the
+        r.upload_scene(sc, noise)           # library's screen is persistent across calls (like the reference's texture)
         half = 5.0 * maze
         cell = rng.integers(0, maze, size=2)
         center = (-half + 10.0 * cell[0] + float(rng.uniform(0.5, 9.5)), float(rng.uniform(-7.5, 1.9)), -half + 10.0 * cell[1] + float(rng.uniform(0.5, 9.5)))
@@ -62,10 +64,12 @@ def against_reference_shader(r, noise, n_poses):
         allc = mm.gen_chunks(W, H, chunk)
         ch = allc[rng.permutation(len(allc))[: gx * gy]].copy()
         if len(ch) < gx * gy:
+            r.close()
             continue
         p = mm.full_frame_params(u, spp=spp, bounce_limit=5, mirror_limit=15)
         p.grid_x, p.grid_y = gx, gy
         img, cnt, _ = r.render(u, p, ch)
+        r.close()
         ref = ref_shader.render(sc, noise, u, p, ch)
         ok = img.tobytes() == ref.tobytes()
         bad += 0 if ok else 1
