@@ -140,7 +140,26 @@ int mm_upload_scene(mm_ctx *ctx, const mm_plane *planes, uint32_t n_planes, cons
     cudaFree(ctx->d_pairs); cudaFree(ctx->d_rects); cudaFree(ctx->d_shade); cudaFree(ctx->d_noise);
     ctx->d_pairs = nullptr; ctx->d_rects = nullptr; ctx->d_shade = nullptr; ctx->d_noise = nullptr;
     const size_t noise_bytes = (size_t)noise_w * noise_h * 4;
-    CK(cudaMalloc(&ctx->d_pairs, prep.pairs.size() * sizeof(PairRec)));
+    {
+        // The kernel forms record addresses as {high word, low word + offset} (one 32-bit add, render_kernel.cu), so the
+        // pair table must not straddle a 4-GB boundary.  An allocation that does is kept until a second one — which then
+        // cannot cover the same boundary — has been made.
+        const size_t pair_bytes = prep.pairs.size() * sizeof(PairRec);
+        void *first = nullptr, *second = nullptr;
+        CK(cudaMalloc(&first, pair_bytes));
+        auto straddles = [&](void *p) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+            return (a >> 32) != ((a + pair_bytes - 1) >> 32);
+        };
+        if (straddles(first)) {
+            cudaError_t e = cudaMalloc(&second, pair_bytes);
+            cudaFree(first);
+            if (e != cudaSuccess) return fail(ctx, MM_ERR_NOMEM, std::string("mm_upload_scene: ") + cudaGetErrorString(e));
+            if (straddles(second)) { cudaFree(second); return fail(ctx, MM_ERR_CUDA, "mm_upload_scene: pair table straddles a 4-GB boundary"); }
+            first = second;
+        }
+        ctx->d_pairs = static_cast<PairRec *>(first);
+    }
     CK(cudaMalloc(&ctx->d_rects, prep.rects.size() * sizeof(RectI)));
     CK(cudaMalloc(&ctx->d_shade, prep.shade.size() * sizeof(RectS)));
     CK(cudaMalloc(&ctx->d_noise, noise_bytes));

@@ -285,6 +285,11 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
     const char *pAB = base + (lit ? 0 : (dir.x < 0.0f ? 32 : 0) + (dir.y < 0.0f ? 64 : 0));
     const char *pZ = base + 128 + ((!lit && dir.z < 0.0f) ? 32 : 0);
     asm("" : "+l"(pAB)); asm("" : "+l"(pZ));      // keep them live: ptxas otherwise re-derives them from sign(dir) at every node
+    // The pair table lies inside one 4-GB-aligned window (checked at upload), so a record address is {hi, lo + offset} with
+    // no carry: one 32-bit add per pointer instead of a 64-bit add (two instructions).
+    uint32_t ab_lo = (uint32_t)reinterpret_cast<uintptr_t>(pAB), z_lo = (uint32_t)reinterpret_cast<uintptr_t>(pZ);
+    uint32_t hi_a = (uint32_t)(reinterpret_cast<uintptr_t>(pAB) >> 32), hi_z = (uint32_t)(reinterpret_cast<uintptr_t>(pZ) >> 32);   // two registers on purpose
+    asm("" : "+r"(ab_lo)); asm("" : "+r"(z_lo)); asm("" : "+r"(hi_a)); asm("" : "+r"(hi_z));
     stack[0] = CUR_END;                        // sentinel: popping an empty stack ends the traversal, no emptiness test
     uint32_t cur = alive ? root : CUR_END, head = 1, slot = beam_slot;
     float t = beam_t;
@@ -302,11 +307,14 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
                     if (!MIXED || !lit) {
                         // 32-B load for (A, B): measured 1.5 % faster than two 16-B loads; folding (Z, link) into a second
                         // 32-B load gave nothing (profiles/r1_block_shape.txt)
-                        const Line32 ab = ldg256(pAB + off);
+                        uint64_t aAB, aZ;
+                        asm("mov.b64 %0, {%1, %2};" : "=l"(aAB) : "r"(ab_lo + cur), "r"(hi_a));
+                        asm("mov.b64 %0, {%1, %2};" : "=l"(aZ) : "r"(z_lo + cur), "r"(hi_z));
+                        const Line32 ab = ldg256(reinterpret_cast<const void *>(aAB));
                         ulonglong2 A, B;
                         A.x = ab.x; A.y = ab.y; B.x = ab.z; B.y = ab.w;
-                        const ulonglong2 Z = __ldg(reinterpret_cast<const ulonglong2 *>(pZ + off));
-                        const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(pZ + off + 16));
+                        const ulonglong2 Z = __ldg(reinterpret_cast<const ulonglong2 *>(aZ));
+                        const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(aZ + 16));
                         inner_step_packed<CNT, RCP>(A, B, Z, lk, k, t, cur, head, stack, tl);
                     } else {
                         const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(base + 144 + off));
