@@ -157,18 +157,18 @@ __device__ __forceinline__ f2 quot2(f2 b, f2 no, f2 nd, f2 r, f2 rl) {
 // dist_k = hit_k ? lo_k : 1e30 (lo_k < t <= 1e30 when hit), `dist1 > dist2` is hit2 && (!hit1 || lo1 > lo2),
 // `dist_near == 1e30` is !hit1 && !hit2 and `dist_far != 1e30` is hit1 && hit2 — the same decisions, fewer instructions.
 template <bool CNT>
-__device__ __forceinline__ void descend(float lo1, float hi1, float lo2, float hi2, const uint2 &lk, float t, uint32_t &cur, uint32_t &head,
-                                        uint32_t *stack, Tally &tl) {
+__device__ __forceinline__ void descend(float lo1, float hi1, float lo2, float hi2, const uint2 &lk, float t, uint32_t &cur, uint32_t *&sp,
+                                        const uint32_t *stack, Tally &tl) {
     const bool hit1 = (hi1 >= lo1) & (lo1 < t) & (hi1 > 0.0f);          // :94
     const bool hit2 = (hi2 >= lo2) & (lo2 < t) & (hi2 > 0.0f);
     const bool swap = hit2 & (!hit1 | (lo1 > lo2));                     // :140, ties keep the left child first
     if (!(hit1 | hit2)) {                                               // :149-150
-        cur = stack[--head];                                            // the bottom entry is the CUR_END sentinel
+        cur = *--sp;                                                    // the bottom entry is the CUR_END sentinel
     } else {                                                            // :151-154
         cur = swap ? lk.y : lk.x;
         if (hit1 & hit2) {
-            stack[head++] = swap ? lk.x : lk.y;
-            if (CNT) tl.max_stack = max(tl.max_stack, head - 1u);       // entries above the sentinel
+            *sp++ = swap ? lk.x : lk.y;
+            if (CNT) tl.max_stack = max(tl.max_stack, (uint32_t)(sp - stack) - 1u);   // entries above the sentinel
         }
     }
 }
@@ -179,7 +179,7 @@ __device__ __forceinline__ void descend(float lo1, float hi1, float lo2, float h
 //   A = (c0.near.x, c0.near.y | c0.far.x, c0.far.y)   B likewise for child 1   Z = (c0.near.z, c1.near.z | c0.far.z, c1.far.z)
 template <bool CNT, bool RCP>
 __device__ __forceinline__ void inner_step_packed(const ulonglong2 &A, const ulonglong2 &B, const ulonglong2 &Z, const uint2 &lk,
-                                                  const RayK &k, float t, uint32_t &cur, uint32_t &head, uint32_t *stack, Tally &tl) {
+                                                  const RayK &k, float t, uint32_t &cur, uint32_t *&sp, const uint32_t *stack, Tally &tl) {
     const f2 an = quot2<RCP>(A.x, k.no_xy, k.nd_xy, k.r_xy, k.rl_xy), af = quot2<RCP>(A.y, k.no_xy, k.nd_xy, k.r_xy, k.rl_xy);
     const f2 bn = quot2<RCP>(B.x, k.no_xy, k.nd_xy, k.r_xy, k.rl_xy), bf = quot2<RCP>(B.y, k.no_xy, k.nd_xy, k.r_xy, k.rl_xy);
     const f2 zn = quot2<RCP>(Z.x, k.no_zz, k.nd_zz, k.r_zz, k.rl_zz), zf = quot2<RCP>(Z.y, k.no_zz, k.nd_zz, k.r_zz, k.rl_zz);
@@ -187,7 +187,7 @@ __device__ __forceinline__ void inner_step_packed(const ulonglong2 &A, const ulo
     const float hi1 = fminf(fminf(lo2f(af), hi2f(af)), lo2f(zf));
     const float lo2 = fmaxf(fmaxf(lo2f(bn), hi2f(bn)), hi2f(zn));
     const float hi2 = fminf(fminf(lo2f(bf), hi2f(bf)), hi2f(zf));
-    descend<CNT>(lo1, hi1, lo2, hi2, lk, t, cur, head, stack, tl);
+    descend<CNT>(lo1, hi1, lo2, hi2, lk, t, cur, sp, stack, tl);
 }
 
 // One interior visit, general form: the literal min/max of shaders.metal:88-93 with NaN-dropping fmin/fmax, for rays whose
@@ -195,8 +195,8 @@ __device__ __forceinline__ void inner_step_packed(const ulonglong2 &A, const ulo
 // Reads the record in its "up" order: a = (c0.min.x, c0.min.y, c0.max.x, c0.max.y), zu = (c0.min.z, c1.min.z, c0.max.z, c1.max.z).
 template <bool CNT, bool RCP>
 __device__ __forceinline__ void inner_step_general(const float4 &a, const float4 &b, const float4 &zu, const uint2 &lk, const Axis &ax,
-                                                   const Axis &ay, const Axis &az, float t, uint32_t &cur, uint32_t &head,
-                                                   uint32_t *stack, Tally &tl) {
+                                                   const Axis &ay, const Axis &az, float t, uint32_t &cur, uint32_t *&sp,
+                                                   const uint32_t *stack, Tally &tl) {
     float t1 = quot<false, RCP>(a.x, ax), t2 = quot<false, RCP>(a.z, ax);
     float lo1 = fminf(t1, t2), hi1 = fmaxf(t1, t2);
     t1 = quot<false, RCP>(a.y, ay); t2 = quot<false, RCP>(a.w, ay);
@@ -209,7 +209,7 @@ __device__ __forceinline__ void inner_step_general(const float4 &a, const float4
     lo2 = fmaxf(lo2, fminf(t1, t2)); hi2 = fminf(hi2, fmaxf(t1, t2));
     t1 = quot<false, RCP>(zu.y, az); t2 = quot<false, RCP>(zu.w, az);
     lo2 = fmaxf(lo2, fminf(t1, t2)); hi2 = fminf(hi2, fmaxf(t1, t2));
-    descend<CNT>(lo1, hi1, lo2, hi2, lk, t, cur, head, stack, tl);
+    descend<CNT>(lo1, hi1, lo2, hi2, lk, t, cur, sp, stack, tl);
 }
 
 // One leaf visit (shaders.metal:127-129 with ray_rect_intersect :51-67 inlined), then pop / finish.
@@ -219,7 +219,7 @@ __device__ __forceinline__ void inner_step_general(const float4 &a, const float4
 // operations the upload used.
 template <bool CNT, bool LITERAL>
 __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 ori, V3 dir, float &t, uint32_t &slot, uint32_t &cur,
-                                          uint32_t &head, const uint32_t *stack, Tally &tl) {
+                                          uint32_t *&sp, Tally &tl) {
     const uint32_t first = cur & 0xFFFFFFu, count = (cur >> 24) & 0x7Fu;
     for (uint32_t i = 0; i < count; i++) {
         const float4 *rp = reinterpret_cast<const float4 *>(rects + first + i);
@@ -245,7 +245,7 @@ __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 or
             slot = first + i;
         }
     }
-    cur = stack[--head];
+    cur = *--sp;
 }
 
 // intersect_bvh_iterative (shaders.metal:115-156) for the rays of one warp.  Every lane of the warp calls this together
@@ -291,7 +291,8 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
     uint32_t hi_a = (uint32_t)(reinterpret_cast<uintptr_t>(pAB) >> 32), hi_z = (uint32_t)(reinterpret_cast<uintptr_t>(pZ) >> 32);   // two registers on purpose
     asm("" : "+r"(ab_lo)); asm("" : "+r"(z_lo)); asm("" : "+r"(hi_a)); asm("" : "+r"(hi_z));
     stack[0] = CUR_END;                        // sentinel: popping an empty stack ends the traversal, no emptiness test
-    uint32_t cur = alive ? root : CUR_END, head = 1, slot = beam_slot;
+    uint32_t *sp = stack + 1;                  // next free entry; a pointer, so push and pop need no address arithmetic
+    uint32_t cur = alive ? root : CUR_END, slot = beam_slot;
     float t = beam_t;
     while (true) {
         const bool isI = (cur & kLeafBit) == 0u;
@@ -315,7 +316,7 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
                         A.x = ab.x; A.y = ab.y; B.x = ab.z; B.y = ab.w;
                         const ulonglong2 Z = __ldg(reinterpret_cast<const ulonglong2 *>(aZ));
                         const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(aZ + 16));
-                        inner_step_packed<CNT, RCP>(A, B, Z, lk, k, t, cur, head, stack, tl);
+                        inner_step_packed<CNT, RCP>(A, B, Z, lk, k, t, cur, sp, stack, tl);
                     } else {
                         const uint2 lk = __ldg(reinterpret_cast<const uint2 *>(base + 144 + off));
                         const float4 a = __ldg(reinterpret_cast<const float4 *>(base + off)), b = __ldg(reinterpret_cast<const float4 *>(base + off + 16));
@@ -324,14 +325,14 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
                         ax.o = ori.x; ax.d = dir.x; ax.r = rx; ax.rl = rlx;
                         ay.o = ori.y; ay.d = dir.y; ay.r = ry; ay.rl = rly;
                         az.o = ori.z; az.d = dir.z; az.r = rz; az.rl = rlz;
-                        inner_step_general<CNT, RCP>(a, b, zu, lk, ax, ay, az, t, cur, head, stack, tl);
+                        inner_step_general<CNT, RCP>(a, b, zu, lk, ax, ay, az, t, cur, sp, stack, tl);
                     }
                 }
             }
         } else {
             if (isL) {
                 if (CNT) tl.leaf++;
-                leaf_step<CNT, MIXED>(rects, ori, dir, t, slot, cur, head, stack, tl);
+                leaf_step<CNT, MIXED>(rects, ori, dir, t, slot, cur, sp, tl);
             }
         }
     }
