@@ -263,6 +263,7 @@ constexpr uint32_t kLeafWeight = MM_LEAF_WEIGHT;   // measured best on B200 (pro
 #define MM_INNER_REPS 4
 #endif
 constexpr uint32_t kInnerReps = MM_INNER_REPS;
+constexpr int kRepUnroll = 2;                      // visits per loop trip: 2 measured best (1: +0.6 %, 4: +1.3 %)
 
 // MIXED = false: no lane of the warp is literal (the common case; the loop then contains no general-form code).
 // Not inlined on purpose: the call boundary parks the path state that the traversal does not touch (throughput,
@@ -300,7 +301,7 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
         const unsigned mI = __ballot_sync(0xFFFFFFFFu, isI), mL = __ballot_sync(0xFFFFFFFFu, isL);
         if ((mI | mL) == 0u) break;
         if (mI != 0u && __popc(mI) >= kLeafWeight * __popc(mL)) {
-#pragma unroll 1
+#pragma unroll kRepUnroll
             for (uint32_t rep = 0; rep < kInnerReps; rep++) {
                 if ((cur & kLeafBit) == 0u) {
                     const size_t off = cur;                      // interior descriptors are byte offsets
