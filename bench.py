@@ -2,20 +2,23 @@
 """bench.py — measures BASELINE.json's metric (Mrays/s and ms/frame at 1080p x 16 spp, 8 bounces) on N B200s.
 
 A step = one frame of the hot path: every rank renders its interleaved share of the frame's 4x4-pixel chunks with the
-CUDA kernel, tiles are all-gathered over NCCL and scattered into the full frame on every rank (N = 1: the kernel writes
-the frame directly).  Total work per step is fixed as N grows ("strong" scaling: one frame, more GPUs).
+CUDA kernel, which stores each finished pixel into every rank's frame through an NVSwitch multicast address / NVLink peer
+mappings (--exchange peer, the default where torch symmetric memory is available) or into a tile buffer that is
+all-gathered over NCCL and scattered (--exchange gather); N = 1: the kernel writes the frame directly.  Total work per
+step is fixed as N grows ("strong" scaling: one frame, more GPUs).
   value / ms_per_step : device time (CUDA events on the launching stream, max over ranks), inputs resident in HBM.
   e2e                 : the same frame through the reference-facing C-ABI call with HOST buffers (mm_render at N = 1:
                         chunk list + uniform host->device, kernel, whole frame device->host), wall clock.
   roofline            : dominant kernel (trace_kernel) — algorithmic node/primitive bytes per launch (SURVEY §8 d:
                         64 B per inner visit, 52 B per rect test, 65 B per shaded hit, 68 B in + 16/spp B out per path)
                         over the kernel's CUDA-event duration, against the measured HBM copy peak as the contract
-                        asks; the scene is on-chip (shared memory / L1 / L2), so the binding limits are reported beside
+                        asks; the scene is on-chip (L1 / L2), so the binding limits are reported beside
                         it: fp32_issue (algorithmic FP32-pipe ops vs SMs x 128 lanes x clock) and the achieved rates.
   cpu_baseline        : the CPU oracle (oracle/mm_oracle.cpp, a port of the reference's shader) on the host cores, on a
                         bounded interleaved crop of the same frame.
---impl reference      : the reference's own CPU implementation of the path = that oracle port (the reference is a
-                        Metal shader + Rust host and cannot be compiled here), all host threads, rank 0 only.
+--impl reference      : the reference's own CPU implementation of the path = that oracle port, all host threads, rank 0
+                        only.  (The reference's shader source does compile as C++ here — oracle/_ref, which pins the port bit
+                        for bit — but it hard-wires 5 bounces and its own grid lookup, so it cannot run this workload.)
 """
 import argparse
 import ctypes

@@ -220,8 +220,8 @@ int mm_present_blur_device(mm_ctx *ctx, const float *d_src, float *d_dst, uint32
 
 /*
  * Micro-benchmarks behind the rooflines of this path (SURVEY §8 d; neither is in MEASURED_PEAKS.json):
- *   MM_MICROBENCH_GATHER  GB/s of useful bytes when every lane fetches the traversal's per-visit pattern (three 16-B
- *                         loads + one 8-B load = 56 B) from random 128-B records of a table of `table_bytes`
+ *   MM_MICROBENCH_GATHER  GB/s of useful bytes when every lane fetches the traversal's per-visit pattern (a 32-B, a 16-B
+ *                         and an 8-B load = 56 B) from random 192-B records of a table of `table_bytes`
  *                         (pass the scene's pair-table size: L1-resident at 32x32, L2-resident at 256x256);
  *   MM_MICROBENCH_FFMA    T lane-instructions/s of dependent-chain-free FP32 FMAs (table_bytes ignored).
  */
