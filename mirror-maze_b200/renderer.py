@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import abi
-from .abi import Counters, Debug, MMError, Params, SceneInfo, Uniform
+from .abi import Counters, Debug, MMError, Params, SceneInfo
 from .host import CHUNK_DTYPE, NODE_DTYPE, PLANE_DTYPE
 
 

@@ -2,7 +2,6 @@
 src/main.rs:91-263, 293-302, 328-352, 357-588, 732-755 and src/maths.rs:139-178.  The reference has no tests, so
 these are: an independent Python restatement (oracle/host_ref.py) compared array for array, structural invariants
 (SURVEY §4), the reference's literals at its own size n = 10, and literal-vs-fast BVH builder equality."""
-import ctypes as C
 import math
 
 import numpy as np

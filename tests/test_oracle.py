@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import CASES, NP_CASES, build_case
+from cases import CASES, build_case
 
 F = np.float32
 HERE = os.path.dirname(os.path.abspath(__file__))

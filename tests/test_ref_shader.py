@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import CASES, REF_SHADER_CASES, build_case
+from cases import REF_SHADER_CASES, build_case
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = json.load(open(os.path.join(HERE, "golden", "golden.json")))

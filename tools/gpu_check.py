@@ -1,6 +1,6 @@
 """Quick GPU bring-up check (developer tool): parity of the CUDA path against the CPU oracle on small cases in every
 kernel mode, then a timing of the north-star configuration.  Run under gpurun."""
-import sys, time, os
+import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mirror_maze_b200 as mm

@@ -2,7 +2,7 @@
 every exchange: NCCL all-gather + scatter, fused NVLink peer stores, fused NVSwitch multicast stores."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch, torch.distributed as dist
+import torch, torch.distributed as dist
 import mirror_maze_b200 as mm
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])

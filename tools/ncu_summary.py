@@ -3,7 +3,7 @@ profiles/ (key metrics, per-SASS-region instruction shares, stall samples).
 
     python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/rN_x_ncu_summary.json --label "..." --command "..."
 """
-import argparse, csv, io, json, subprocess, sys
+import argparse, csv, io, json, subprocess
 
 METRICS = [
     "gpu__time_duration.sum", "sm__cycles_elapsed.avg", "smsp__inst_executed.sum", "sm__inst_executed.avg.per_cycle_active",
@@ -36,8 +36,6 @@ def main():
     for n, u, v in zip(names, units, vals):
         if n in METRICS:
             metrics[n] = {"unit": u, "value": v}
-        if n.startswith("smsp__pcsamp_warps_issue_stalled") and not n.endswith("_not_issued"):
-            pass
 
     src = list(csv.reader(io.StringIO(ncu_csv(a.rep, "source"))))
     h = next(i for i, r in enumerate(src) if r and r[0] == "Address")
