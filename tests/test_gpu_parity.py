@@ -470,3 +470,23 @@ def test_roofline_microbenchmarks(renderer):
     assert 500.0 < renderer.microbench(0, 94 * 1024) < 40000.0         # GB/s of useful bytes, L1-resident table
     assert 500.0 < renderer.microbench(0, 6 * 1024 * 1024) < 40000.0   # L2-resident table
     assert 10.0 < renderer.microbench(1) < 40.0                        # T lane-instr/s (148 SMs x 128 lanes x <= 1.965 GHz = 37.2)
+
+
+def test_multi_gpu_frame_equals_single_gpu_frame_for_every_exchange():
+    """tools/mgpu_check.py under torchrun on two GPUs, when the box has them: the N-GPU frame through the NCCL gather,
+    the fused NVLink peer stores and the fused NVSwitch multicast stores, each bit-identical to the one-GPU frame."""
+    import socket
+    import subprocess
+    import sys
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    root = os.path.dirname(HERE)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tools", "mgpu_check.py")]
+    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MULTI-GPU PARITY OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
