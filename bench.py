@@ -151,6 +151,30 @@ def cpu_reference_run(a, steps, warmup, threads=0):
     return rays / total / 1e6, {"cores": cores, "sample": sample, "ms_per_step": 1e3 * total / max(1, steps), "rays_per_step": rays // max(1, steps)}
 
 
+def reference_shader_on_its_own_dispatch():
+    """The compiled reference shader (oracle/_ref) and the port, timed on the one workload the unmodified shader can run at
+    scale: its own dispatch (10x10 maze, 1024x768, 64 spp, 5 bounces, 768 chunks).  Informational: shows that the port the
+    reference arm times is not slower than the reference's own code.  None when the library is not present."""
+    try:
+        import mirror_maze_b200 as mm
+        from oracle import oracle, ref_shader
+        if not ref_shader.available():
+            return None
+        noise = mm.load_noise()
+        scene = mm.MazeScene(10, 0)
+        u = mm.default_uniform(10, 1024, 768, 4, 3)
+        p = mm.full_frame_params(u, spp=64, bounce_limit=5, mirror_limit=15)
+        p.grid_x, p.grid_y = 32, 24
+        chunks = mm.gen_chunks(1024, 768, 4)[: 32 * 24].copy()
+        t0 = time.perf_counter(); img, cnt, _ = oracle.render(scene, noise, u, p, chunks); t_port = time.perf_counter() - t0
+        t0 = time.perf_counter(); ref = ref_shader.render(scene, noise, u, p, chunks); t_ref = time.perf_counter() - t0
+        return {"workload": "the reference's own dispatch: 10x10 maze, 1024x768, 64 spp, 5 bounces, 768 chunks", "rays": cnt["rays"],
+                "reference_shader_Mrays_s": round(cnt["rays"] / t_ref / 1e6, 3), "port_Mrays_s": round(cnt["rays"] / t_port / 1e6, 3),
+                "images_identical": bool(img.tobytes() == ref.tobytes())}
+    except Exception as e:                      # informational only
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -162,6 +186,9 @@ def run_reference(a):
             "data": "synthetic", "config": {"workload": workload_name(a), "note": "ms_per_step is for the bounded sample, not the whole frame"},
             "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"], "why_port": WHY_PORT},
             "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    check = reference_shader_on_its_own_dispatch()
+    if check is not None:
+        line["cpu_baseline"]["reference_shader_check"] = check
     print(json.dumps(line), flush=True)
     return 0
 
