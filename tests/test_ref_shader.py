@@ -21,7 +21,9 @@ GOLDEN = json.load(open(os.path.join(HERE, "golden", "golden.json")))
 
 @pytest.fixture(scope="module")
 def ref():
-    from oracle import ref_shader
+    from oracle import oracle as o, ref_shader
+    if not ref_shader.available():
+        o.build()                       # make -C oracle also builds _ref/libref_shader.so where /root/reference exists
     if not ref_shader.available():
         pytest.skip("oracle/_ref/libref_shader.so not built (needs /root/reference)")
     L = ref_shader.lib()
