@@ -12,6 +12,8 @@
  * byte-identical to the reference's #[repr(C)] types (src/main.rs:32-90, src/maths.rs:3-16,50-52).
  *
  * Threading: a context is not thread-safe; it owns one CUDA device, one stream and all device memory.
+ * mm_multi (below) is the same over a list of devices in one process: it owns one context per device, the peer
+ * mappings between them and, optionally, the NCCL communicators of the tile gather.
  * Errors: every function returns 0 on success or a negative MM_ERR_* code and never aborts or throws
  * across the ABI (the reference panics through .expect()/.unwrap(), e.g. src/utils.rs:19,43).
  */
@@ -78,6 +80,8 @@ typedef struct mm_params {
 
 #define MM_FLAG_COUNTERS      1u   /* fill mm_counters beyond `rays` (slower kernel variant)          */
 #define MM_FLAG_FORCE_LITERAL 2u   /* use the literal-divide traversal for every ray (validation)     */
+#define MM_FLAG_NO_ZERO_COPY 128u  /* mm_render / mm_render_async: copy the screen with a DMA transfer even when out_rgba is mapped pinned
+                                      memory the kernel could store into directly (for comparisons)                        */
 #define MM_FLAG_RCP_SLAB     64u   /* opt-in arithmetic variant: slab quotients (b - o) * RN(1/d) instead of the literal
                                       (b - o) / d of shaders.metal:88-93 — what a fast-math compile of the shader amounts to.
                                       NOT the default; the oracle implements the same rule under the same flag and the
@@ -116,8 +120,10 @@ typedef struct mm_debug {
 #define MM_ERR_UNSUPPORTED   -5   /* spp not a power of two <= 256, chunk_width^2*spp > limits, ...  */
 #define MM_ERR_NOMEM         -6
 
-#define MM_MAX_STACK 48           /* traversal stack entries on the device (reference: 50, unchecked,
-                                     shaders.metal:123); BVH depth is validated against it at upload  */
+#define MM_MAX_STACK 52           /* device traversal stack: the reference's 50 entries (unchecked, shaders.metal:123) plus
+                                     a bottom sentinel, rounded up.  Occupancy <= BVH depth - 1, so every tree the
+                                     reference's stack can hold (depth <= 51) uploads; deeper ones return MM_ERR_BVH */
+#define MM_MAX_BVH_DEPTH 51
 
 typedef struct mm_ctx mm_ctx;
 
@@ -144,16 +150,44 @@ int mm_upload_scene(mm_ctx *ctx,
 
 /*
  * Replaces copy_to_buf(pixel_data) + set_bytes(uni) + dispatch_thread_groups (main.rs:784, 867-886) and the
- * read-back of the screen texture.  Synchronous.  `chunks` has grid_x*grid_y entries.  The context owns a
- * persistent device screen image, the counterpart of the reference's GPU-private screen texture
- * (main.rs:702-709): created zero-filled at first use (and again when the view size changes), written only
+ * read-back of the screen texture.  Synchronous.  `chunks` has grid_x*grid_y entries; chunks == NULL keeps the list of the
+ * previous call / mm_set_chunks (the reference rewrites the buffer every frame, utils.rs:96-102; a full-frame caller
+ * need not).  The context owns a persistent device screen image, the counterpart of the reference's GPU-private screen
+ * texture (main.rs:702-709): created zero-filled at first use (and again when the view size changes), written only
  * at the pixels of the chunks a call renders, kept across calls.  out_rgba is a HOST buffer of
- * view_height*view_width*4 floats, row-major [y][x][rgba], that receives a copy of the whole screen image
- * after the kernel; out_rgba may be null when the caller reads the screen later (mm_present).  counters/debug may be null.
+ * view_height*view_width*4 floats, row-major [y][x][rgba]; it may be null when the caller reads the screen later
+ * (mm_present).  counters/debug may be null.  How out_rgba is filled depends on the memory it lies in:
+ *   - mapped pinned memory (from mm_host_alloc / mm_host_register, or pinned by the caller's own CUDA allocator): ZERO-COPY —
+ *     the kernel stores every pixel it finishes straight into out_rgba over PCIe while it traces, no copy follows.  Only
+ *     the pixels of the chunks this call renders are written: out_rgba is then the caller's persistent copy of the
+ *     screen, exactly like the reference's texture, and equals the device screen as long as every dispatch since the
+ *     screen was created went into the same buffer.  MM_FLAG_NO_ZERO_COPY selects a DMA copy of the whole screen instead.
+ *   - any other (pageable) memory, e.g. a Rust Vec<f32>: the whole screen is DMA-copied into a pinned staging buffer of
+ *     the context and memcpy'd to out_rgba (what a pageable caller really pays; register the Vec once with
+ *     mm_host_register to avoid it).
  */
 int mm_render(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params,
               const mm_chunk *chunks, uint32_t n_chunks,
               float *out_rgba, mm_counters *counters, const mm_debug *debug);
+/*
+ * The same without the wait: the reference's frame loop commits and goes on (commit() without wait_until_completed,
+ * main.rs:894).  mm_render_async returns once the frame is enqueued; out_rgba (and the debug arrays) are valid after
+ * mm_wait, which also returns the frame's counters.  One host-buffer frame is in flight per context: a second
+ * mm_render_async waits for the first.  mm_render == mm_render_async + mm_wait.
+ */
+int mm_render_async(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params,
+                    const mm_chunk *chunks, uint32_t n_chunks, float *out_rgba, const mm_debug *debug);
+int mm_wait(mm_ctx *ctx, mm_counters *counters);
+/*
+ * Pinned, device-mapped host memory for frames (the counterpart of the reference's StorageModeManaged buffers,
+ * utils.rs:86-94): mm_host_alloc allocates it, mm_host_register pins and maps memory the caller already owns (a
+ * Vec<f32>'s buffer; it must stay allocated until mm_host_unregister).  Process-wide, usable with every context and
+ * device.  A frame buffer from here makes mm_render's output zero-copy (above).
+ */
+int mm_host_alloc(size_t bytes, void **out);
+int mm_host_free(void *ptr);
+int mm_host_register(void *ptr, size_t bytes);
+int mm_host_unregister(void *ptr);
 
 /*
  * Device-resident variants for callers that keep frames on the GPU (multi-GPU tile gather, frame batching).
@@ -187,11 +221,15 @@ int mm_scatter_gathered_device(mm_ctx *ctx, const mm_uniform *uni, const mm_para
 #define MM_MAX_PEERS 8
 int mm_render_peers_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params,
                            float *const *frames, uint32_t n_frames);
+/* The same through ONE NVSwitch multicast address mapped over every rank's frame (e.g. torch symmetric memory's
+ * multicast_ptr): each pixel is one `multimem.st` that the switch replicates into all frames — the only instruction
+ * family PTX defines for multicast addresses; plain stores to one are undefined. */
+int mm_render_multicast_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, float *mc_frame);
 int mm_sync(mm_ctx *ctx);
 /* Run the context's work on a caller-owned cudaStream_t (e.g. torch's current stream) from now on; NULL
  * restores the context's own stream.  The caller keeps the stream alive while the context uses it. */
 int mm_set_stream(mm_ctx *ctx, void *stream);
-/* Counters of the most recent mm_render_device (valid after mm_sync). */
+/* Counters of the most recent render launch; waits for that launch's (asynchronous) counter copy, not for the stream. */
 int mm_last_counters(mm_ctx *ctx, mm_counters *out);
 /* Device time of the most recent render kernel in milliseconds (CUDA events on the context's stream). */
 int mm_last_ms(mm_ctx *ctx, float *ms);
@@ -244,6 +282,50 @@ int mm_selftest_quotient(mm_ctx *ctx, uint64_t n_pairs, uint64_t seed, uint64_t 
  * Host-only, no GPU needed.
  */
 int mm_rect_edge_thresholds(float length, float *lo, float *up);
+
+/* ---- One process, several GPUs (SURVEY §8 b/e) ---------------------------------------------------------------------- */
+
+/*
+ * The reference drives one device from one thread (main.rs:616-623, 867-894).  mm_multi splits the same dispatch over a
+ * list of CUDA devices inside ONE process, behind the same kind of calls: the scene is replicated on every device, the
+ * frame's virtual groups are interleaved over the devices (device i renders groups i, i+n, ...; seeds depend on the group
+ * index, so the assembled frame is bit-identical to a one-device frame), and the finished pixels are exchanged by
+ *   MM_EXCHANGE_PEER  (default) the render kernel itself: every device's kernel stores each pixel it finishes into the
+ *                     frame buffers of ALL devices through NVLink peer mappings (cudaDeviceEnablePeerAccess);
+ *   MM_EXCHANGE_NCCL  tiles gathered with ncclAllGather over communicators from ncclCommInitAll (libnccl is loaded
+ *                     at run time, only for this mode), then one scatter launch per device;
+ *   MM_EXCHANGE_NONE  no device-side exchange: every device keeps only its own pixels; the frame is assembled in the
+ *                     caller's mapped pinned host buffer by the kernels' zero-copy stores (n PCIe links in parallel).
+ * out_rgba as for mm_render: a mapped pinned buffer is written by all kernels directly (zero-copy, every mode); any
+ * other buffer gets device 0's assembled frame through a staged copy (not available with MM_EXCHANGE_NONE).
+ */
+typedef struct mm_multi mm_multi;
+#define MM_EXCHANGE_PEER 0
+#define MM_EXCHANGE_NCCL 1
+#define MM_EXCHANGE_NONE 2
+int mm_multi_create(const int *cuda_devices, int n_devices, int exchange, mm_multi **out);
+int mm_multi_destroy(mm_multi *m);
+const char *mm_multi_last_error(const mm_multi *m);     /* m == NULL: last mm_multi_create error */
+int mm_multi_n_devices(const mm_multi *m);
+int mm_multi_upload_scene(mm_multi *m,
+                          const mm_plane *planes, uint32_t n_planes,
+                          const mm_bvh_node *nodes, uint32_t n_nodes,
+                          const uint32_t *indices, const uint8_t *materials, const mm_float4 *emissions,
+                          const uint8_t *noise_rgba8, uint32_t noise_w, uint32_t noise_h);
+/* One frame over all devices.  params->group_first/step/count are ignored (the library partitions the whole grid).
+ * counters: sums over the devices (max for max_stack).  mm_multi_render == mm_multi_render_async + mm_multi_wait. */
+int mm_multi_render(mm_multi *m, const mm_uniform *uni, const mm_params *params,
+                    const mm_chunk *chunks, uint32_t n_chunks, float *out_rgba, mm_counters *counters);
+int mm_multi_render_async(mm_multi *m, const mm_uniform *uni, const mm_params *params,
+                          const mm_chunk *chunks, uint32_t n_chunks, float *out_rgba);
+int mm_multi_wait(mm_multi *m, mm_counters *counters);
+/* After mm_multi_wait: device `index`'s frame buffer (H*W*4 floats on that device; the whole frame with
+ * MM_EXCHANGE_PEER / MM_EXCHANGE_NCCL, only that device's pixels with MM_EXCHANGE_NONE). */
+int mm_multi_frame_device(mm_multi *m, int index, float **d_frame);
+/* Slowest device's render-kernel time of the last frame, ms (CUDA events on each device's stream). */
+int mm_multi_last_ms(mm_multi *m, float *ms);
+/* The per-device context (scene info, microbenchmarks); owned by m. */
+mm_ctx *mm_multi_ctx(mm_multi *m, int index);
 
 /* ---- Host surface kept from the reference (restated in C++; no device work) ------------------------- */
 

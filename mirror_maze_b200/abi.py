@@ -1,7 +1,7 @@
 """ctypes binding of include/mirror_maze_cuda.h (the C-ABI drop-in boundary).
 
 Struct layouts are the reference's #[repr(C)] types (reference src/main.rs:32-90, src/maths.rs:3-16,50-52); sizes
-are asserted at import.  The library is built in-tree by `make -C mirror-maze_b200` (see __graft_entry__.build).
+are asserted at import.  The library is built in-tree by `make -C mirror_maze_b200` (see __graft_entry__.build).
 """
 import ctypes as C
 import os
@@ -9,10 +9,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libmirror_maze_cuda.so"
 
-MAX_STACK = 48
+MAX_STACK = 52
+MAX_BVH_DEPTH = 51
 FLAG_COUNTERS = 1
 FLAG_FORCE_LITERAL = 2
 FLAG_RCP_SLAB = 64
+FLAG_NO_ZERO_COPY = 128
+EXCHANGE_PEER, EXCHANGE_NCCL, EXCHANGE_NONE = 0, 1, 2
+MAX_PEERS = 8
 
 ERR_NAMES = {0: "MM_OK", -1: "MM_ERR_INVALID", -2: "MM_ERR_CUDA", -3: "MM_ERR_NO_SCENE", -4: "MM_ERR_BVH",
              -5: "MM_ERR_UNSUPPORTED", -6: "MM_ERR_NOMEM"}
@@ -100,6 +104,24 @@ PROTOTYPES = {
     "mm_last_error": (C.c_char_p, [_vp]),
     "mm_upload_scene": (C.c_int, [_vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32]),
     "mm_render": (C.c_int, [_vp, _P(Uniform), _P(Params), _vp, C.c_uint32, _vp, _P(Counters), _P(Debug)]),
+    "mm_render_async": (C.c_int, [_vp, _P(Uniform), _P(Params), _vp, C.c_uint32, _vp, _P(Debug)]),
+    "mm_wait": (C.c_int, [_vp, _P(Counters)]),
+    "mm_host_alloc": (C.c_int, [C.c_size_t, _P(_vp)]),
+    "mm_host_free": (C.c_int, [_vp]),
+    "mm_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "mm_host_unregister": (C.c_int, [_vp]),
+    "mm_render_multicast_device": (C.c_int, [_vp, _P(Uniform), _P(Params), _vp]),
+    "mm_multi_create": (C.c_int, [_P(C.c_int), C.c_int, C.c_int, _P(_vp)]),
+    "mm_multi_destroy": (C.c_int, [_vp]),
+    "mm_multi_last_error": (C.c_char_p, [_vp]),
+    "mm_multi_n_devices": (C.c_int, [_vp]),
+    "mm_multi_upload_scene": (C.c_int, [_vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32]),
+    "mm_multi_render": (C.c_int, [_vp, _P(Uniform), _P(Params), _vp, C.c_uint32, _vp, _P(Counters)]),
+    "mm_multi_render_async": (C.c_int, [_vp, _P(Uniform), _P(Params), _vp, C.c_uint32, _vp]),
+    "mm_multi_wait": (C.c_int, [_vp, _P(Counters)]),
+    "mm_multi_frame_device": (C.c_int, [_vp, C.c_int, _P(_vp)]),
+    "mm_multi_last_ms": (C.c_int, [_vp, _P(C.c_float)]),
+    "mm_multi_ctx": (_vp, [_vp, C.c_int]),
     "mm_set_chunks": (C.c_int, [_vp, _vp, C.c_uint32]),
     "mm_render_device": (C.c_int, [_vp, _P(Uniform), _P(Params), _vp, _vp]),
     "mm_scatter_tiles_device": (C.c_int, [_vp, _P(Uniform), _P(Params), _vp, _vp]),

@@ -6,60 +6,50 @@
 #include <cstring>
 #include <new>
 #include <string>
-#include "render_kernel.cuh"
 #include "scene_prep.h"
 
 using namespace mmk;
 
-struct mm_ctx {
-    int device = -1;
-    cudaStream_t stream = nullptr;       // stream in use
-    cudaStream_t own_stream = nullptr;   // created by mm_create
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool timed = false;
-    std::string err;
-    int n_sms = 0;
-    size_t smem_optin = 0;
-    // scene
-    bool have_scene = false;
-    PairRec *d_pairs = nullptr;
-    RectI *d_rects = nullptr;
-    RectS *d_shade = nullptr;
-    uint8_t *d_noise = nullptr;
-    uint32_t n_pairs = 0, n_slots = 0, n_nodes = 0, root_link = 0, root_count = 0, depth = 0, max_leaf = 0, noise_w = 0, noise_h = 0;
-    bool fast_ok = false, rect_fast_ok = false;
-    // per-frame
-    mm_chunk *d_chunks = nullptr;
-    uint32_t chunks_cap = 0, n_chunks = 0;
-    Counters *d_counters = nullptr;
-    Counters *h_counters = nullptr;   // pinned
-    float *d_screen = nullptr;        // persistent screen image (the reference's private screen texture, main.rs:702-709)
-    float *d_screen2 = nullptr;       // ping-pong partner for the present blur
-    uint32_t screen_w = 0, screen_h = 0;
-    uint32_t *d_dbg_u32[3] = {nullptr, nullptr, nullptr};
-    float *d_dbg_rad = nullptr;
-    size_t dbg_cap = 0;
-    // last launch facts
-    uint32_t last_smem = 0, last_blocks_per_sm = 0, last_block_threads = 0;
-    const void *cfg_fn = nullptr;     // kernel variant whose attributes / occupancy were last set up
-    size_t cfg_smem = 0;
-};
+#include <mutex>
+#include <vector>
+#include "ctx.h"
 
-static std::string g_create_err;
+static thread_local std::string g_create_err;
 
-#define CK(call)                                                                                          \
-    do {                                                                                                  \
-        cudaError_t e__ = (call);                                                                         \
-        if (e__ != cudaSuccess) {                                                                         \
-            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                               \
-            return MM_ERR_CUDA;                                                                           \
-        }                                                                                                 \
-    } while (0)
+#define CK(call) MM_CK(call)
 
-static int fail(mm_ctx *ctx, int code, const std::string &msg) {
+namespace mmapi {
+int fail(mm_ctx *ctx, int code, const std::string &msg) {
     ctx->err = msg;
     return code;
 }
+
+// Mapped pinned host memory the library knows about (mm_host_alloc / mm_host_register): process-wide, any context.
+struct HostRange { uintptr_t base; size_t bytes; bool owned; uintptr_t dev; };
+static std::mutex g_host_mu;
+static std::vector<HostRange> g_host;
+
+void *host_device_alias(const void *p, size_t bytes) {
+    if (!p || bytes == 0) return nullptr;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    {
+        std::lock_guard<std::mutex> lock(g_host_mu);
+        for (const HostRange &r : g_host)
+            if (a >= r.base && a + bytes <= r.base + r.bytes) return reinterpret_cast<void *>(r.dev + (a - r.base));
+    }
+    // pinned by someone else (cudaHostAlloc / cudaHostRegister in the caller, e.g. a torch pinned tensor): under unified
+    // addressing such memory is mapped too; accept it when both ends of the range resolve to one contiguous device alias
+    cudaPointerAttributes a0, a1;
+    if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || cudaPointerGetAttributes(&a1, reinterpret_cast<const char *>(p) + bytes - 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer || !a1.devicePointer) return nullptr;
+    if (reinterpret_cast<uintptr_t>(a1.devicePointer) - reinterpret_cast<uintptr_t>(a0.devicePointer) != bytes - 1) return nullptr;
+    return a0.devicePointer;
+}
+}  // namespace mmapi
+using mmapi::fail;
 
 extern "C" {
 
@@ -86,6 +76,7 @@ int mm_create(int cuda_device, mm_ctx **out) {
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     bool ok = cudaSetDevice(cuda_device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev2, cudaEventDisableTiming) == cudaSuccess &&
               cudaMalloc(&ctx->d_counters, sizeof(Counters)) == cudaSuccess &&
               cudaMallocHost(&ctx->h_counters, sizeof(Counters)) == cudaSuccess;
     if (!ok) {
@@ -110,6 +101,9 @@ int mm_destroy(mm_ctx *ctx) {
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    cudaFree(ctx->d_screen8);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return MM_OK;
@@ -195,14 +189,7 @@ int mm_set_chunks(mm_ctx *ctx, const mm_chunk *chunks, uint32_t n_chunks) {
 
 }  // extern "C"
 
-namespace {
-
-struct Launch {
-    KParams p;
-    KernelChoice choice;
-    unsigned blocks;
-    size_t smem;
-};
+namespace mmapi {
 
 int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool debug, Launch &L) {
     if (!uni || !par) return fail(ctx, MM_ERR_INVALID, "null uniform or params");
@@ -275,6 +262,7 @@ int do_launch(mm_ctx *ctx, Launch &L) {
     CK(launch_trace(L.p, L.choice, L.blocks, L.smem, ctx->stream));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));      // mm_last_counters waits on this, not on the whole stream
     ctx->timed = true;
     return MM_OK;
 }
@@ -296,7 +284,8 @@ void counters_out(const Counters *h, mm_counters *o) {
     o->rect_tests = h->rect_tests; o->hits = h->hits; o->literal_rays = h->literal_rays; o->max_stack = h->max_stack;
 }
 
-}  // namespace
+}  // namespace mmapi
+using namespace mmapi;
 
 extern "C" {
 
@@ -310,6 +299,20 @@ int mm_render_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params
     if (rc != MM_OK) return rc;
     L.p.image = d_image;
     L.p.tiles = d_tiles;
+    return do_launch(ctx, L);
+}
+
+int mm_render_multicast_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, float *mc_frame) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!mc_frame) return fail(ctx, MM_ERR_INVALID, "mm_render_multicast_device: null multicast address");
+    CK(cudaSetDevice(ctx->device));
+    Launch L;
+    int rc = build_launch(ctx, uni, params, false, L);
+    if (rc != MM_OK) return rc;
+    L.p.n_peers = 1;
+    L.p.peers[0] = mc_frame;
+    L.p.peers_multicast = 1;
     return do_launch(ctx, L);
 }
 
@@ -330,12 +333,80 @@ int mm_render_peers_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *
     return do_launch(ctx, L);
 }
 
-int mm_render(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, const mm_chunk *chunks, uint32_t n_chunks,
-              float *out_rgba, mm_counters *counters, const mm_debug *debug) {
+/* ---- pinned host memory the kernel can write into directly ------------------------------------------------------------ */
+
+int mm_host_alloc(size_t bytes, void **out) {
+    if (!out || bytes == 0) return MM_ERR_INVALID;
+    *out = nullptr;
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return MM_ERR_NOMEM; }
+    void *d = nullptr;
+    if (cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(p); return MM_ERR_CUDA; }
+    {
+        std::lock_guard<std::mutex> lock(g_host_mu);
+        g_host.push_back({reinterpret_cast<uintptr_t>(p), bytes, true, reinterpret_cast<uintptr_t>(d)});
+    }
+    *out = p;
+    return MM_OK;
+}
+
+int mm_host_register(void *ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return MM_ERR_INVALID;
+    if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) { cudaGetLastError(); return MM_ERR_CUDA; }
+    void *d = nullptr;
+    if (cudaHostGetDevicePointer(&d, ptr, 0) != cudaSuccess) { cudaGetLastError(); cudaHostUnregister(ptr); return MM_ERR_CUDA; }
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    g_host.push_back({reinterpret_cast<uintptr_t>(ptr), bytes, false, reinterpret_cast<uintptr_t>(d)});
+    return MM_OK;
+}
+
+static int host_release(void *ptr, bool owned) {
+    if (!ptr) return MM_OK;
+    {
+        std::lock_guard<std::mutex> lock(g_host_mu);
+        size_t i = 0;
+        for (; i < g_host.size(); i++)
+            if (g_host[i].base == reinterpret_cast<uintptr_t>(ptr) && g_host[i].owned == owned) break;
+        if (i == g_host.size()) return MM_ERR_INVALID;
+        g_host.erase(g_host.begin() + (long)i);
+    }
+    cudaError_t e = owned ? cudaFreeHost(ptr) : cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return MM_ERR_CUDA; }
+    return MM_OK;
+}
+int mm_host_free(void *ptr) { return host_release(ptr, true); }
+int mm_host_unregister(void *ptr) { return host_release(ptr, false); }
+
+/* ---- host-buffer frames ------------------------------------------------------------------------------------------------ */
+
+int mm_wait(mm_ctx *ctx, mm_counters *counters) {
     if (!ctx) return MM_ERR_INVALID;
     ctx->err.clear();
-    int rc = mm_set_chunks(ctx, chunks, n_chunks);
-    if (rc != MM_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->pending_out) {                              // staged frame: pinned staging -> the caller's (pageable) buffer
+        memcpy(ctx->pending_out, ctx->h_stage, ctx->pending_bytes);
+        ctx->pending_out = nullptr;
+    }
+    ctx->in_flight = false;
+    if (counters) {
+        if (!ctx->timed) return fail(ctx, MM_ERR_INVALID, "mm_wait: nothing rendered yet");
+        counters_out(ctx->h_counters, counters);
+    }
+    return MM_OK;
+}
+
+int mm_render_async(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, const mm_chunk *chunks, uint32_t n_chunks,
+                    float *out_rgba, const mm_debug *debug) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    int rc;
+    if (ctx->in_flight && (rc = mm_wait(ctx, nullptr)) != MM_OK) return rc;     // one host-buffer frame in flight per context
+    if (chunks) {
+        if ((rc = mm_set_chunks(ctx, chunks, n_chunks)) != MM_OK) return rc;
+    } else if (ctx->n_chunks == 0) {
+        return fail(ctx, MM_ERR_INVALID, "mm_render: null chunk list and none set earlier");
+    }
     const bool dbg = debug && (debug->first_hit || debug->segments || debug->mirror_hits || debug->radiance);
     Launch L;
     rc = build_launch(ctx, uni, params, dbg, L);
@@ -343,6 +414,13 @@ int mm_render(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, const
     rc = ensure_screen(ctx, L.p.W, L.p.H);
     if (rc != MM_OK) return rc;
     L.p.image = ctx->d_screen;
+    const size_t frame_bytes = (size_t)L.p.W * L.p.H * 4 * sizeof(float);
+    // Zero-copy output: a caller buffer inside mapped pinned memory (mm_host_alloc / mm_host_register) is written by the
+    // kernel itself, pixel by pixel over PCIe while it traces; no screen copy follows.
+    void *pinned = out_rgba ? host_device_alias(out_rgba, frame_bytes) : nullptr;
+    void *alias = (params->flags & MM_FLAG_NO_ZERO_COPY) ? nullptr : pinned;
+    L.p.host_out = static_cast<float *>(alias);
+    ctx->last_zero_copy = alias ? 1u : 0u;
     const size_t n_paths = (size_t)L.p.total_paths;
     if (dbg) {
         if (n_paths > ctx->dbg_cap) {
@@ -358,18 +436,38 @@ int mm_render(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, const
         L.p.dbg_mirror_hits = debug->mirror_hits ? ctx->d_dbg_u32[2] : nullptr;
         L.p.dbg_radiance = debug->radiance ? ctx->d_dbg_rad : nullptr;
     }
+    const bool staged = out_rgba && !pinned;
+    if (staged && ctx->stage_bytes < frame_bytes) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->stage_bytes = 0;
+        CK(cudaMallocHost(&ctx->h_stage, frame_bytes));
+        ctx->stage_bytes = frame_bytes;
+    }
     rc = do_launch(ctx, L);
     if (rc != MM_OK) return rc;
-    if (out_rgba) CK(cudaMemcpyAsync(out_rgba, ctx->d_screen, (size_t)L.p.W * L.p.H * 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->in_flight = true;
+    if (out_rgba && !alias) {
+        // the whole persistent screen: DMA into the caller's pinned buffer, or into the library's pinned staging buffer
+        // when the caller's memory is not known to be pinned (copied on to it by mm_wait)
+        float *dst = staged ? ctx->h_stage : out_rgba;
+        CK(cudaMemcpyAsync(dst, ctx->d_screen, frame_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (staged) { ctx->pending_out = out_rgba; ctx->pending_bytes = frame_bytes; }
+    }
     if (dbg) {
         if (debug->first_hit) CK(cudaMemcpyAsync(debug->first_hit, ctx->d_dbg_u32[0], n_paths * 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (debug->segments) CK(cudaMemcpyAsync(debug->segments, ctx->d_dbg_u32[1], n_paths * 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (debug->mirror_hits) CK(cudaMemcpyAsync(debug->mirror_hits, ctx->d_dbg_u32[2], n_paths * 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (debug->radiance) CK(cudaMemcpyAsync(debug->radiance, ctx->d_dbg_rad, n_paths * 12, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (counters) counters_out(ctx->h_counters, counters);
     return MM_OK;
+}
+
+int mm_render(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, const mm_chunk *chunks, uint32_t n_chunks,
+              float *out_rgba, mm_counters *counters, const mm_debug *debug) {
+    int rc = mm_render_async(ctx, uni, params, chunks, n_chunks, out_rgba, debug);
+    if (rc != MM_OK) return rc;
+    return mm_wait(ctx, counters);
 }
 
 int mm_scatter_tiles_device(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params, const float *d_tiles, float *d_image) {
@@ -502,6 +600,9 @@ int mm_selftest_quotient(mm_ctx *ctx, uint64_t n_pairs, uint64_t seed, uint64_t 
 
 int mm_last_counters(mm_ctx *ctx, mm_counters *out) {
     if (!ctx || !out) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!ctx->timed) return fail(ctx, MM_ERR_INVALID, "mm_last_counters: nothing rendered yet");
+    CK(cudaEventSynchronize(ctx->ev2));              // the asynchronous counter copy of the last launch has landed
     counters_out(ctx->h_counters, out);
     return MM_OK;
 }

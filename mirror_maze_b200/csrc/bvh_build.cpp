@@ -193,7 +193,8 @@ void build_bvh_fast(const std::vector<mm_plane> &planes, std::vector<mm_bvh_node
     build(planes, nodes, indices, true);
 }
 
-bool bvh_stats(const mm_bvh_node *nodes, uint32_t n_nodes, uint32_t n_planes, uint32_t *depth_out, uint32_t *max_leaf_out) {
+bool bvh_stats(const mm_bvh_node *nodes, uint32_t n_nodes, uint32_t n_planes, uint32_t *depth_out, uint32_t *max_leaf_out,
+               std::vector<uint8_t> *reachable) {
     if (n_nodes == 0) return false;
     std::vector<uint8_t> seen(n_nodes, 0);
     std::vector<std::pair<uint32_t, uint32_t>> stack;   // (node, depth)
@@ -217,6 +218,7 @@ bool bvh_stats(const mm_bvh_node *nodes, uint32_t n_nodes, uint32_t n_planes, ui
     }
     if (depth_out) *depth_out = depth;
     if (max_leaf_out) *max_leaf_out = max_leaf;
+    if (reachable) reachable->swap(seen);
     return true;
 }
 

@@ -56,6 +56,8 @@ void build_bvh_literal(const std::vector<mm_plane> &planes, std::vector<mm_bvh_n
 void build_bvh_fast(const std::vector<mm_plane> &planes, std::vector<mm_bvh_node> &nodes, std::vector<uint32_t> &indices);
 
 // Structural facts used by upload-time validation.  Returns false on malformed trees.
-bool bvh_stats(const mm_bvh_node *nodes, uint32_t n_nodes, uint32_t n_planes, uint32_t *depth, uint32_t *max_leaf);
+// `reachable` (optional): n_nodes flags, 1 for every node the walk from the root visits.
+bool bvh_stats(const mm_bvh_node *nodes, uint32_t n_nodes, uint32_t n_planes, uint32_t *depth, uint32_t *max_leaf,
+               std::vector<uint8_t> *reachable = nullptr);
 
 }  // namespace mmh

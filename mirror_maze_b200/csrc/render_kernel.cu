@@ -520,9 +520,15 @@ trace_kernel(const __grid_constant__ KParams P) {
         const float4 px = make_float4(fdiv(sx, d), fdiv(sy, d), fdiv(sz, d), 1.0f);
         if (P.image && pxx < P.W && pxy < P.H) reinterpret_cast<float4 *>(P.image)[(size_t)pxy * P.W + pxx] = px;
         if (P.tiles) reinterpret_cast<float4 *>(P.tiles)[(size_t)k * P.ppc + (flat >> P.log2_spp)] = px;
-        if (P.n_peers && pxx < P.W && pxy < P.H) {                      // fused exchange: NVLink peer / NVSwitch multicast stores
+        if ((P.n_peers || P.host_out) && pxx < P.W && pxy < P.H) {
             const size_t at = (size_t)pxy * P.W + pxx;
-            for (uint32_t i = 0; i < P.n_peers; i++) reinterpret_cast<float4 *>(P.peers[i])[at] = px;
+            if (P.host_out) reinterpret_cast<float4 *>(P.host_out)[at] = px;        // zero-copy output: mapped pinned host frame, over PCIe
+            if (P.peers_multicast) {                                    // fused exchange, NVSwitch multicast: one store, replicated by the switch
+                float4 *mc = reinterpret_cast<float4 *>(P.peers[0]) + at;
+                asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(px.x), "f"(px.y), "f"(px.z), "f"(px.w) : "memory");
+            } else {                                                    // fused exchange, NVLink peer mappings: one store per rank's frame
+                for (uint32_t i = 0; i < P.n_peers; i++) reinterpret_cast<float4 *>(P.peers[i])[at] = px;
+            }
         }
     }
 

@@ -77,6 +77,8 @@ struct KParams {
     float *tiles;              // may be null
     float *peers[MM_MAX_PEERS];  // extra frames every finished pixel is stored into (peer-mapped or multicast), n_peers used
     uint32_t n_peers;
+    uint32_t peers_multicast;  // peers[0] is an NVSwitch multicast address: stored with multimem.st, the only defined access to one
+    float *host_out;           // mapped pinned host frame every finished pixel is also stored into (zero-copy output); may be null
     Counters *counters;
     uint32_t *dbg_first_hit, *dbg_segments, *dbg_mirror_hits;
     float *dbg_radiance;

@@ -50,12 +50,13 @@ int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *
                   const uint32_t *indices, const uint8_t *materials, const mm_float4 *emissions, Prepared &out,
                   std::string &err) {
     uint32_t depth = 0, max_leaf = 0;
-    if (!mmh::bvh_stats(nodes, n_nodes, n_planes, &depth, &max_leaf)) {
+    std::vector<uint8_t> reachable;   // nodes the traversal can reach; a caller may pass a capacity-sized array with a garbage tail
+    if (!mmh::bvh_stats(nodes, n_nodes, n_planes, &depth, &max_leaf, &reachable)) {
         err = "malformed BVH: child or leaf range out of bounds, shared child or cycle";
         return MM_ERR_BVH;
     }
-    if (depth > MM_MAX_STACK) {   // stack occupancy <= depth - 1, plus the kernel's bottom sentinel
-        err = "BVH depth " + std::to_string(depth) + " exceeds MM_MAX_STACK";
+    if (depth > MM_MAX_BVH_DEPTH) {   // stack occupancy <= depth - 1 <= 50 (the reference's stack), plus the kernel's bottom sentinel
+        err = "BVH depth " + std::to_string(depth) + " exceeds MM_MAX_BVH_DEPTH";
         return MM_ERR_BVH;
     }
     if (max_leaf > kMaxLeafCount || n_planes >= (1u << 24) || n_nodes >= (1u << 24)) {
@@ -65,11 +66,11 @@ int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *
     for (uint32_t i = 0; i < n_planes; i++)
         if (indices[i] >= n_planes) { err = "index out of range"; return MM_ERR_BVH; }
 
-    // pair ids: interior nodes in node-index order (the root, node 0, gets pair 0)
+    // pair ids: reachable interior nodes in node-index order (the root, node 0, gets pair 0); unreachable entries are never read
     std::vector<uint32_t> pair_id(n_nodes, 0xFFFFFFFFu);
     uint32_t n_pairs = 0;
     for (uint32_t i = 0; i < n_nodes; i++)
-        if (nodes[i].tri_count == 0) pair_id[i] = n_pairs++;
+        if (reachable[i] && nodes[i].tri_count == 0) pair_id[i] = n_pairs++;
     auto desc = [&](uint32_t c) -> uint32_t {
         const mm_bvh_node &nd = nodes[c];
         return nd.tri_count > 0 ? (kLeafBit | nd.left_first | (nd.tri_count << 24)) : pair_id[c] * (uint32_t)sizeof(PairRec);
@@ -78,7 +79,7 @@ int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *
     std::memset(out.pairs.data(), 0, out.pairs.size() * sizeof(PairRec));
     bool fast_ok = true;
     for (uint32_t i = 0; i < n_nodes; i++) {
-        if (nodes[i].tri_count != 0) continue;
+        if (!reachable[i] || nodes[i].tri_count != 0) continue;
         const mm_bvh_node &a = nodes[nodes[i].left_first], &b = nodes[nodes[i].left_first + 1];
         PairRec &p = out.pairs[pair_id[i]];
         for (int sy = 0; sy < 2; sy++)

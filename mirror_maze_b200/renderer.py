@@ -42,6 +42,38 @@ def scatter_tiles_host(tiles, chunks, first, step, count, chunk_width, image):
     return image
 
 
+class HostFrame:
+    """A frame buffer in mapped pinned host memory (mm_host_alloc): mm_render / mm_multi_render write into it zero-copy.
+    `array` is the [H, W, 4] float32 view; keep the HostFrame alive while the array is in use."""
+
+    def __init__(self, height, width):
+        self._lib = abi.load_library()
+        self._ptr = C.c_void_p()
+        self.nbytes = int(height) * int(width) * 16
+        rc = self._lib.mm_host_alloc(self.nbytes, C.byref(self._ptr))
+        if rc != 0:
+            raise MMError(rc, "mm_host_alloc")
+        buf = (C.c_float * (self.nbytes // 4)).from_address(self._ptr.value)
+        self.array = np.ctypeslib.as_array(buf).reshape(int(height), int(width), 4)
+        self.array[...] = 0.0
+
+    @property
+    def ptr(self):
+        return self._ptr.value
+
+    def close(self):
+        if getattr(self, "_ptr", None) and self._ptr.value:
+            self.array = None
+            self._lib.mm_host_free(self._ptr)
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Renderer:
     def __init__(self, device=0):
         self._lib = abi.load_library()
@@ -107,11 +139,25 @@ class Renderer:
         return out, cnt.as_dict(), dbg
 
     def render_into(self, uniform, params, chunks_ptr, n_chunks, out_ptr):
-        """mm_render on raw host pointers (pinned buffers of the caller); returns counters dict."""
+        """mm_render on raw host pointers; returns counters dict.  chunks_ptr None keeps the device chunk list."""
         cnt = Counters()
         self._ck(self._lib.mm_render(self._ctx, C.byref(uniform), C.byref(params), chunks_ptr, n_chunks, out_ptr,
                                      C.byref(cnt), None))
         return cnt.as_dict()
+
+    def render_async(self, uniform, params, chunks_ptr, n_chunks, out_ptr):
+        """mm_render_async: returns once the frame is enqueued (the reference commits without waiting, main.rs:894)."""
+        self._ck(self._lib.mm_render_async(self._ctx, C.byref(uniform), C.byref(params), chunks_ptr, n_chunks, out_ptr, None))
+
+    def wait(self):
+        """mm_wait: the frame of the last render_async is in the caller's buffer; returns its counters."""
+        cnt = Counters()
+        self._ck(self._lib.mm_wait(self._ctx, C.byref(cnt)))
+        return cnt.as_dict()
+
+    def render_multicast_device(self, uniform, params, mc_ptr):
+        """mm_render_multicast_device: every finished pixel is one multimem.st to an NVSwitch multicast address."""
+        self._ck(self._lib.mm_render_multicast_device(self._ctx, C.byref(uniform), C.byref(params), mc_ptr))
 
     # -- device-resident path ------------------------------------------------------------------------------------
     def set_stream(self, cuda_stream_ptr):
@@ -173,6 +219,78 @@ class Renderer:
         return float(ms.value)
 
 
+class MultiRenderer:
+    """mm_multi: one process, several GPUs behind the C-ABI (no torch involved): scene replicated, the frame's groups
+    interleaved over the devices, pixels exchanged by the render kernel's peer stores ("peer"), an NCCL all-gather of
+    tiles ("nccl") or assembled only in the caller's pinned host frame ("none")."""
+
+    EXCHANGE = {"peer": abi.EXCHANGE_PEER, "nccl": abi.EXCHANGE_NCCL, "none": abi.EXCHANGE_NONE}
+
+    def __init__(self, devices, exchange="peer"):
+        self._lib = abi.load_library()
+        self._m = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        rc = self._lib.mm_multi_create(devs, len(devices), self.EXCHANGE[exchange], C.byref(self._m))
+        if rc != 0:
+            raise MMError(rc, (self._lib.mm_multi_last_error(None) or b"").decode())
+        self.devices, self.exchange = list(devices), exchange
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._lib.mm_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MMError(rc, (self._lib.mm_multi_last_error(self._m) or b"").decode())
+
+    def upload_scene(self, scene, noise):
+        planes = np.ascontiguousarray(scene.planes, dtype=PLANE_DTYPE)
+        nodes = np.ascontiguousarray(scene.nodes, dtype=NODE_DTYPE)
+        indices = np.ascontiguousarray(scene.indices, dtype=np.uint32)
+        materials = np.ascontiguousarray(scene.materials, dtype=np.uint8)
+        emissions = np.ascontiguousarray(scene.emissions, dtype=np.float32)
+        noise = np.ascontiguousarray(noise, dtype=np.uint8)
+        nh, nw = noise.shape[:2]
+        self._ck(self._lib.mm_multi_upload_scene(self._m, planes.ctypes.data, len(planes), nodes.ctypes.data, len(nodes),
+                                                 indices.ctypes.data, materials.ctypes.data, emissions.ctypes.data,
+                                                 noise.ctypes.data, nw, nh))
+
+    def render(self, uniform, params, chunks, out):
+        """One frame over all devices into the host array / HostFrame `out`; returns the summed counters."""
+        chunks_ptr, n = (None, 0) if chunks is None else (np.ascontiguousarray(chunks, dtype=CHUNK_DTYPE), len(chunks))
+        self._chunks = chunks_ptr
+        cnt = Counters()
+        out_ptr = out.ptr if isinstance(out, HostFrame) else out.ctypes.data
+        self._ck(self._lib.mm_multi_render(self._m, C.byref(uniform), C.byref(params), None if chunks_ptr is None else chunks_ptr.ctypes.data,
+                                           n, out_ptr, C.byref(cnt)))
+        return cnt.as_dict()
+
+    def render_async(self, uniform, params, chunks, out_ptr):
+        chunks_ptr, n = (None, 0) if chunks is None else (np.ascontiguousarray(chunks, dtype=CHUNK_DTYPE), len(chunks))
+        self._chunks = chunks_ptr
+        self._ck(self._lib.mm_multi_render_async(self._m, C.byref(uniform), C.byref(params),
+                                                 None if chunks_ptr is None else chunks_ptr.ctypes.data, n, out_ptr))
+
+    def wait(self):
+        cnt = Counters()
+        self._ck(self._lib.mm_multi_wait(self._m, C.byref(cnt)))
+        return cnt.as_dict()
+
+    def frame_device_ptr(self, index):
+        p = C.c_void_p()
+        self._ck(self._lib.mm_multi_frame_device(self._m, index, C.byref(p)))
+        return p.value
+
+    def last_ms(self):
+        ms = C.c_float()
+        self._ck(self._lib.mm_multi_last_ms(self._m, C.byref(ms)))
+        return float(ms.value)
+
+
 class TiledFrameRenderer:
     """One rank of the multi-GPU frame: scene replicated, groups interleaved over ranks.
 
@@ -212,7 +330,7 @@ class TiledFrameRenderer:
         # default stream's handle is 0, which mm_set_stream reads as "use the context's own stream").
         self.stream = torch.cuda.Stream(dev)
         self.exchange, self.exchange_note = "none", ""
-        self.handle, self.peer_ptrs = None, None
+        self.handle, self.peer_ptrs, self.multicast_ptr = None, None, 0
         if world > 1 and exchange in ("auto", "peer"):
             try:
                 self._setup_peer_frames(dev, multicast)
@@ -240,8 +358,9 @@ class TiledFrameRenderer:
         self.image.zero_()
         self.handle = symm.rendezvous(self.image, self.dist.group.WORLD)
         mc = int(self.handle.multicast_ptr) if multicast else 0
+        self.multicast_ptr = mc
         if mc:
-            self.peer_ptrs, self.exchange_note = [mc], "NVSwitch multicast stores"
+            self.peer_ptrs, self.exchange_note = [mc], "NVSwitch multicast stores (multimem.st)"
         else:
             self.peer_ptrs, self.exchange_note = [int(p) for p in self.handle.buffer_ptrs], "NVLink peer stores"
         self.torch.cuda.synchronize(dev)
@@ -257,7 +376,10 @@ class TiledFrameRenderer:
             with self.torch.cuda.stream(self.stream):
                 self.handle.barrier(channel=0)          # every rank is done reading its previous frame
             if self.my.group_count:
-                self.r.render_peers_device(u, self.my, self.peer_ptrs)
+                if self.multicast_ptr:
+                    self.r.render_multicast_device(u, self.my, self.multicast_ptr)
+                else:
+                    self.r.render_peers_device(u, self.my, self.peer_ptrs)
             with self.torch.cuda.stream(self.stream):
                 self.handle.barrier(channel=1)          # every rank's stores have landed in this rank's frame
             return self.image

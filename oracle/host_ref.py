@@ -3,7 +3,7 @@
 Follows reference src/main.rs:328-352 (TreeBuilder), :357-396 (Kruskal), :397-438 (walls), :443-586 (scene),
 :91-263 (BVH) and the published algorithms of rand 0.8.5 / rand_chacha 0.3.1 / rand_core 0.6.4 (Cargo.lock:342-371;
 NOT vendored under /root/reference, so the RNG stream is PARITY UNPINNED against a real `cargo run`).
-Used by tests/test_host_surface.py to cross-check the C++ restatement in mirror-maze_b200/csrc array for array at small n.
+Used by tests/test_host_surface.py to cross-check the C++ restatement in mirror_maze_b200/csrc array for array at small n.
 All scene arithmetic is numpy float32 (one rounding per operation).
 """
 import numpy as np

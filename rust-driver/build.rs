@@ -3,12 +3,12 @@
 use std::process::Command;
 
 fn main() {
-    let dir = std::path::Path::new(env!("CARGO_MANIFEST_DIR")).join("../mirror-maze_b200");
+    let dir = std::path::Path::new(env!("CARGO_MANIFEST_DIR")).join("../mirror_maze_b200");
     let status = Command::new("make").arg("-C").arg(&dir).arg("libmirror_maze_cuda.so").status().expect("make not found");
     assert!(status.success(), "building libmirror_maze_cuda.so failed");
     println!("cargo:rustc-link-search=native={}", dir.display());
     println!("cargo:rustc-link-lib=dylib=mirror_maze_cuda");
     println!("cargo:rustc-link-arg=-Wl,-rpath,{}", dir.display());
-    println!("cargo:rerun-if-changed=../mirror-maze_b200/csrc");
+    println!("cargo:rerun-if-changed=../mirror_maze_b200/csrc");
     println!("cargo:rerun-if-changed=../include/mirror_maze_cuda.h");
 }

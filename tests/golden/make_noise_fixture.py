@@ -1,4 +1,4 @@
-"""Regenerates mirror-maze_b200/assets/noiseTexture-2.rgba8.gz from the reference's PNG (run in the authoring
+"""Regenerates mirror_maze_b200/assets/noiseTexture-2.rgba8.gz from the reference's PNG (run in the authoring
 container only; /root/reference does not exist on the GPU box).
 
 The reference embeds textures/noiseTexture-2.png (src/main.rs:354) and uploads its bitmap as a 512x512 RGBA8Unorm
@@ -12,7 +12,7 @@ import sys
 from PIL import Image
 
 SRC = "/root/reference/textures/noiseTexture-2.png"
-DST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "mirror-maze_b200", "assets", "noiseTexture-2.rgba8.gz")
+DST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "mirror_maze_b200", "assets", "noiseTexture-2.rgba8.gz")
 
 if __name__ == "__main__":
     im = Image.open(SRC).convert("RGBA")

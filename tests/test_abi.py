@@ -80,12 +80,17 @@ def test_null_arguments_are_errors_not_crashes(mm):
 
 def test_product_never_imports_oracle():
     """The product path must not route through oracle/ (parity claims would be void)."""
-    pkg = os.path.join(ROOT, "mirror-maze_b200")
+    pkg = os.path.join(ROOT, "mirror_maze_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cpp", ".cu", ".h", ".cuh")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 for needle in ("libmm_oracle", "from oracle", "import oracle", "np_oracle", "mmo_render", "oracle/_ref", "dlopen"):
+                    if needle == "dlopen" and f == "multi.cu":
+                        # the one run-time load in the product: libnccl for MM_EXCHANGE_NCCL, and nothing else
+                        libs = re.findall(r'"([^"]*\.so[^"]*)"', text)
+                        assert libs and all(name.startswith("libnccl.so") for name in libs), libs
+                        continue
                     assert needle not in text, f"{f} references the oracle ({needle})"
                 assert not re.search(r'#include\s*["<][^">]*oracle', text), f"{f} includes oracle code"
 
@@ -108,7 +113,7 @@ def test_packed_fp32_instruction_mix_shows_no_contraction():
     FADD2 : FMUL2 : FFMA2 = 2 : 2 : 3.  A fused or dropped instruction changes the ratio."""
     import shutil
     import subprocess
-    obj = os.path.join(ROOT, "mirror-maze_b200", "build", "render_kernel.o")
+    obj = os.path.join(ROOT, "mirror_maze_b200", "build", "render_kernel.o")
     tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     if not (os.path.exists(obj) and os.path.exists(tool)):
         pytest.skip("needs the built render_kernel.o and cuobjdump")

@@ -103,37 +103,6 @@ def test_tile_partition_equals_full_frame(mm, oracle, noise, scenes, renderer):
         r2.close()
 
 
-def test_device_tiles_gather_and_scatter(mm, noise, scenes, renderer):
-    """mm_render_device -> tiles, then mm_scatter_tiles_device, as the NCCL path uses them (world emulated on one GPU)."""
-    import torch
-
-    sc, u, p, ch = build_case(mm, "yaw", scenes)
-    renderer.upload_scene(sc, noise)
-    full = renderer.render(u, p, ch)[0]
-    dev = torch.device("cuda", 0)
-    r2 = mm.Renderer(0)
-    r2.upload_scene(sc, noise)
-    r2.set_chunks(ch)
-    world = 4
-    parts = [mm.tile_partition(p.grid_x * p.grid_y, r, world) for r in range(world)]
-    ppc = u.chunk_width ** 2
-    max_count = max(pt[2] for pt in parts)
-    gathered = torch.zeros((world, max_count, ppc, 4), dtype=torch.float32, device=dev)
-    for rank in range(world):
-        q = mm.Params.from_buffer_copy(bytes(p))
-        q.group_first, q.group_step, q.group_count = parts[rank]
-        r2.render_device(u, q, tiles_ptr=gathered[rank].data_ptr())
-    image = torch.zeros((int(u.view_height), int(u.view_width), 4), dtype=torch.float32, device=dev)
-    for rank in range(world):
-        q = mm.Params.from_buffer_copy(bytes(p))
-        q.group_first, q.group_step, q.group_count = parts[rank]
-        r2.scatter_tiles_device(u, q, gathered[rank].data_ptr(), image.data_ptr())
-    r2.sync()
-    torch.cuda.synchronize()
-    assert image.cpu().numpy().tobytes() == full.tobytes()
-    r2.close()
-
-
 def test_fused_exchange_stores_every_pixel_into_every_frame(mm, noise, scenes, renderer):
     """mm_render_peers_device, as the multi-GPU peer/multicast exchange uses it (ranks emulated on one GPU, the 'peer'
     frames are plain local buffers): after every rank's launch, each frame holds the whole single-call frame."""
@@ -490,3 +459,212 @@ def test_multi_gpu_frame_equals_single_gpu_frame_for_every_exchange():
            "--master-port", str(port), os.path.join(root, "tools", "mgpu_check.py")]
     out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MULTI-GPU PARITY OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+# ---- full-size frame coordinates of the other BASELINE configurations (crops checked against the oracle) ----------------
+
+FULL_SIZE = {
+    # north-star headline: 64x64 maze, 1080p x 16 spp x 8 bounces
+    "hl64": dict(maze=64, W=1920, H=1080, spp=16, bounce=8),
+    # BASELINE configs[2]: 64x64 maze, 3840x2160, 64 spp (T = 1024 threads per virtual group), 16 bounces
+    "cfg3": dict(maze=64, W=3840, H=2160, spp=64, bounce=16),
+    # BASELINE configs[3]: 256x256 maze (43.6 k planes, BVH depth 21), 1080p x 16 spp x 8 bounces
+    "cfg4": dict(maze=256, W=1920, H=1080, spp=16, bounce=8),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FULL_SIZE))
+def test_full_size_crops_match_oracle(mm, oracle, noise, scenes, name):
+    """The real frame coordinates of the 64x64 headline, config 3 and config 4: crops of chunk groups at the first, a middle
+    and the last chunk columns of the full-size virtual grid (so the largest texid values and the u32 wraps of
+    texid * 15823 / texid * 9737333 in the seed, shaders.metal:298, are the real ones), every observable bit-identical."""
+    c = FULL_SIZE[name]
+    sc = scenes(c["maze"])
+    u = mm.default_uniform(c["maze"], c["W"], c["H"], 4)
+    ch = mm.gen_chunks(c["W"], c["H"], 4)
+    p = mm.full_frame_params(u, spp=c["spp"], bounce_limit=c["bounce"])
+    n_groups = p.grid_x * p.grid_y
+    col = c["H"] // 4                                            # groups per chunk column (gen_pixels order: x outer, y inner)
+    count = 96 if c["spp"] >= 64 else 270
+    r = mm.Renderer(0)                                           # fresh zero-filled screen
+    r.upload_scene(sc, noise)
+    for first in (0, (n_groups // 2 // col) * col + col // 3, n_groups - count):
+        q = mm.Params.from_buffer_copy(bytes(p))
+        q.group_first, q.group_step, q.group_count = first, 1, count
+        ref_img = np.zeros((c["H"], c["W"], 4), dtype=np.float32)
+        ref = oracle.render(sc, noise, u, q, ch, debug=True, out=ref_img)
+        got = r.render(u, q, ch, debug=True)
+        m = ref[0][..., 3] == 1
+        assert m.sum() == count * 16
+        assert got[0][m].tobytes() == ref[0][m].tobytes(), f"{name}: crop at group {first}"
+        assert_same((ref[0], got[1], got[2]), ref)
+    # a strided sample over the whole grid as well (every 997th group: all chunk rows and columns)
+    q = mm.Params.from_buffer_copy(bytes(p))
+    q.group_first, q.group_step = 5, 997
+    q.group_count = (n_groups - 5 + 996) // 997
+    if c["spp"] >= 64:
+        q.group_step = 4999; q.group_count = (n_groups - 5 + 4998) // 4999
+    ref = oracle.render(sc, noise, u, q, ch, debug=True)
+    got = r.render(u, q, ch, debug=True)
+    m = ref[0][..., 3] == 1
+    assert got[0][m].tobytes() == ref[0][m].tobytes()
+    assert_same((ref[0], got[1], got[2]), ref)
+    r.close()
+
+
+def test_zero_copy_async_and_staged_host_frames_are_identical(mm, noise, scenes):
+    """mm_render into (a) a pageable numpy array (staged copy), (b) a mapped pinned HostFrame (the kernel's zero-copy stores),
+    (c) the same with MM_FLAG_NO_ZERO_COPY (DMA copy), (d) mm_render_async + mm_wait with a kept chunk list (chunks = NULL),
+    (e) a caller-registered buffer (mm_host_register): all the same bits."""
+    import ctypes as C
+
+    sc, u, p, ch = build_case(mm, "cfg2_small", scenes)
+    r = mm.Renderer(0)
+    r.upload_scene(sc, noise)
+    H, W = int(u.view_height), int(u.view_width)
+    a, ca, _ = r.render(u, p, ch)                                       # (a)
+    hf = mm.HostFrame(H, W)
+    chunks = np.ascontiguousarray(ch)
+    cb = r.render_into(u, p, chunks.ctypes.data, len(chunks), hf.ptr)   # (b)
+    assert hf.array.tobytes() == a.tobytes() and cb == ca
+    hf.array[...] = -1.0
+    q = mm.Params.from_buffer_copy(bytes(p)); q.flags = mm.FLAG_NO_ZERO_COPY
+    r.render_into(u, q, chunks.ctypes.data, len(chunks), hf.ptr)        # (c)
+    assert hf.array.tobytes() == a.tobytes()
+    hf.array[...] = -1.0
+    r.render_async(u, p, None, 0, hf.ptr)                               # (d) chunk list kept from the previous call
+    cd = r.wait()
+    assert hf.array.tobytes() == a.tobytes() and cd == ca
+    mine = np.full((H, W, 4), -1.0, dtype=np.float32)                   # (e)
+    lib = mm.load_library()
+    assert lib.mm_host_register(mine.ctypes.data, mine.nbytes) == 0
+    r.render_into(u, p, None, 0, mine.ctypes.data)
+    assert lib.mm_host_unregister(mine.ctypes.data) == 0
+    assert mine.tobytes() == a.tobytes()
+    # zero-copy writes only the chunks a dispatch renders: the buffer is the caller's persistent copy of the screen
+    hf.array[...] = 0.0
+    half = mm.Params.from_buffer_copy(bytes(p))
+    half.group_first, half.group_step, half.group_count = 0, 2, (p.grid_x * p.grid_y + 1) // 2
+    r2 = mm.Renderer(0)
+    r2.upload_scene(sc, noise)
+    r2.render_into(u, half, chunks.ctypes.data, len(chunks), hf.ptr)
+    half.group_first, half.group_count = 1, (p.grid_x * p.grid_y) // 2
+    r2.render_into(u, half, None, 0, hf.ptr)
+    assert hf.array.tobytes() == a.tobytes()
+    r2.close(); r.close(); hf.close()
+
+
+def test_deep_and_padded_bvh(mm, oracle, noise):
+    """A skewed BVH of depth 51 (stack occupancy 50: all the reference's stack holds, shaders.metal:123) renders like the
+    oracle; depth 52 is refused with MM_ERR_BVH; a node array passed at its 2n-1 capacity with an unreachable garbage tail
+    uploads and renders the same frame."""
+    import types
+    from mirror_maze_b200.host import PLANE_DTYPE, NODE_DTYPE
+
+    def chain(n_planes):
+        # planes side by side along x; node 2k+1 = leaf k, node 2k+2 = the rest: depth n_planes
+        P = np.zeros(n_planes, dtype=PLANE_DTYPE)
+        for i in range(n_planes):
+            P[i]["origin"], P[i]["v"], P[i]["u"], P[i]["color"] = [-60.0 + 2.5 * i, 6.0, 30.0], [2.0, 0.0, 0.0], [0.0, -12.0, 0.0], [0.6, 0.5, 0.4]
+        lo = np.array([[P[i]["origin"][0], -6.0, 30.0] for i in range(n_planes)], dtype=np.float32)
+        hi = np.array([[P[i]["origin"][0] + 2.0, 6.0, 30.0] for i in range(n_planes)], dtype=np.float32)
+        nodes = np.zeros(2 * n_planes - 1, dtype=NODE_DTYPE)
+        def box(i, a, b):
+            nodes[i]["aabb_min"], nodes[i]["aabb_max"] = lo[a:b].min(axis=0), hi[a:b].max(axis=0)
+        at, k = 0, 0
+        while True:
+            box(at, k, n_planes)
+            if n_planes - k == 1:
+                nodes[at]["left_first"], nodes[at]["tri_count"] = k, 1
+                break
+            nodes[at]["left_first"], nodes[at]["tri_count"] = 2 * k + 1, 0
+            box(2 * k + 1, k, k + 1)
+            nodes[2 * k + 1]["left_first"], nodes[2 * k + 1]["tri_count"] = k, 1
+            at, k = 2 * k + 2, k + 1
+        return types.SimpleNamespace(planes=P, nodes=nodes, indices=np.arange(n_planes, dtype=np.uint32),
+                                     materials=(np.arange(n_planes) % 3 == 0).astype(np.uint8),
+                                     emissions=np.tile(np.array([[1.0, 0.8, 0.3, 1.0]], dtype=np.float32), (n_planes, 1)))
+
+    u = mm.default_uniform(10, 64, 32, 4, camera_center=(0.0, 0.0, 0.0))
+    ch = mm.gen_chunks(64, 32, 4)
+    p = mm.full_frame_params(u, spp=8, bounce_limit=4)
+    r = mm.Renderer(0)
+    s51 = chain(51)
+    r.upload_scene(s51, noise)
+    assert r.scene_info()["bvh_depth"] == 51 == mm.MAX_BVH_DEPTH
+    ref = oracle.render(s51, noise, u, p, ch, debug=True)
+    assert_same(r.render(u, p, ch, debug=True), ref)
+    with pytest.raises(mm.MMError) as e:
+        r.upload_scene(chain(52), noise)
+    assert e.value.code == -4
+    padded = chain(51)
+    tail = np.zeros(40, dtype=NODE_DTYPE)
+    tail["left_first"] = 0xFFFFFF00                                  # garbage interior nodes nobody reaches
+    padded.nodes = np.concatenate([padded.nodes, tail])
+    r.upload_scene(padded, noise)
+    assert r.render(u, p, ch)[0].tobytes() == ref[0].tobytes()
+    r.close()
+
+
+def _multi_frames(mm, noise, sc, u, p, ch, devices, exchange):
+    H, W = int(u.view_height), int(u.view_width)
+    m = mm.MultiRenderer(devices, exchange)
+    m.upload_scene(sc, noise)
+    hf = mm.HostFrame(H, W)
+    cnt = m.render(u, p, ch, hf)                                  # zero-copy assembly in pinned host memory
+    pinned = hf.array.copy()
+    paged = np.zeros((H, W, 4), dtype=np.float32)
+    cnt2 = None
+    if exchange != "none" or len(devices) == 1:
+        cnt2 = m.render(u, p, None, paged)                        # staged copy of device 0's assembled frame
+    ms = m.last_ms()
+    m.close(); hf.close()
+    return pinned, paged, cnt, cnt2, ms
+
+
+def test_multi_context_on_one_device_equals_single_context(mm, noise, scenes, renderer):
+    """mm_multi over a one-device list: the same frame and counters as mm_render."""
+    sc, u, p, ch = build_case(mm, "ragged", scenes)
+    renderer.upload_scene(sc, noise)
+    q = mm.Params.from_buffer_copy(bytes(p)); q.flags = mm.FLAG_COUNTERS
+    r = mm.Renderer(0); r.upload_scene(sc, noise)
+    full, cnt, _ = r.render(u, q, ch)
+    r.close()
+    pinned, paged, c1, c2, ms = _multi_frames(mm, noise, sc, u, q, ch, [0], "peer")
+    assert pinned.tobytes() == full.tobytes() and paged.tobytes() == full.tobytes()
+    assert c1 == cnt and c2 == cnt and ms > 0
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl", "none"])
+def test_multi_gpu_one_process_frame_equals_single_gpu_frame(mm, noise, scenes, exchange):
+    """mm_multi (one process, no torch in the data path): the frame split over every visible GPU (2..8) is bit-identical to
+    the one-GPU frame, for the fused peer-store exchange, the NCCL tile gather and host-only assembly; counters add up."""
+    import torch
+
+    n = min(torch.cuda.device_count(), 8)
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    sc, u, p, ch = build_case(mm, "cfg2_small", scenes)
+    q = mm.Params.from_buffer_copy(bytes(p)); q.flags = mm.FLAG_COUNTERS
+    r = mm.Renderer(0); r.upload_scene(sc, noise)
+    full, cnt, _ = r.render(u, q, ch)
+    r.close()
+    for devs in ([0, 1], list(range(n))):
+        pinned, paged, c1, c2, ms = _multi_frames(mm, noise, sc, u, q, ch, devs, exchange)
+        assert pinned.tobytes() == full.tobytes(), (exchange, devs)
+        assert c1 == cnt
+        if c2 is not None:
+            assert paged.tobytes() == full.tobytes() and c2 == cnt
+        # device-resident frames: every device holds the whole frame after a peer / nccl exchange
+        if exchange != "none":
+            m = mm.MultiRenderer(devs, exchange); m.upload_scene(sc, noise)
+            hf = mm.HostFrame(int(u.view_height), int(u.view_width))
+            m.render(u, q, ch, hf)
+            for i, d in enumerate(devs):
+                t = torch.empty((int(u.view_height), int(u.view_width), 4), dtype=torch.float32, device=f"cuda:{d}")
+                with torch.cuda.device(d):
+                    import ctypes as C
+                    cudart = torch.cuda.cudart()
+                    assert int(cudart.cudaMemcpy(t.data_ptr(), m.frame_device_ptr(i), t.numel() * 4, 3)) == 0   # cudaMemcpyDeviceToDevice
+                assert t.cpu().numpy().tobytes() == full.tobytes(), (exchange, d)
+            m.close(); hf.close()
