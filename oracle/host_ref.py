@@ -245,3 +245,56 @@ def build_scene(n, seed=0):
     nodes, indices = build_bvh(P)
     return {"grid": grid, "vert": np.array(vert, dtype=F).reshape(-1, 3), "hori": np.array(hori, dtype=F).reshape(-1, 3),
             "planes": P, "materials": mats, "emissions": emis, "nodes": nodes, "indices": indices}
+
+
+# ---- frame inputs without the product library (bench.py --impl reference) -------------------------------------------------
+# The reference's start-of-run camera / uniform (src/main.rs:732-755, maths.rs:139-156) and chunk order (:293-302), generalised
+# to n x n like the product's mm_default_uniform / mm_gen_chunks, in plain Python + libm (the same sinf / cosf / asinf the
+# C++ host surface calls), so the reference arm of bench.py builds its whole workload with no product .so mapped.
+# tests/test_host_surface.py checks both against the product's, byte for byte.
+
+def _libm():
+    import ctypes
+    import ctypes.util
+    m = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    for name in ("sinf", "cosf", "asinf"):
+        f = getattr(m, name)
+        f.restype, f.argtypes = ctypes.c_float, [ctypes.c_float]
+    return m
+
+
+def calculate_quaternion(direction):
+    """maths.rs:139-156 in float32."""
+    m = _libm()
+    d = np.asarray(direction, dtype=F)
+    mag = lambda v: F(np.sqrt(F(F(F(v[0] * v[0]) + F(v[1] * v[1])) + F(v[2] * v[2]))))
+    cam = np.array([F(d[0] / mag(d)), F(d[1] / mag(d)), F(d[2] / mag(d))], dtype=F)
+    z = np.array([0.0, 0.0, 1.0], dtype=F)
+    axis = np.array([F(F(z[1] * cam[2]) - F(z[2] * cam[1])), F(F(z[2] * cam[0]) - F(z[0] * cam[2])), F(F(z[0] * cam[1]) - F(z[1] * cam[0]))], dtype=F)
+    la = mag(axis)
+    axis_n = np.array([F(axis[0] / la), F(axis[1] / la), F(axis[2] / la)], dtype=F)
+    half_theta = F(F(m.asinf(float(la))) / F(2.0))
+    s, c = F(m.sinf(float(half_theta))), F(m.cosf(float(half_theta)))
+    return np.array([F(axis_n[0] * s), F(axis_n[1] * s), F(axis_n[2] * s), c], dtype=F)
+
+
+def default_uniform_bytes(maze_n, view_width, view_height, chunk_width=4, time=0):
+    """The 56-byte `Uniform` (main.rs:41-49) of the start pose, as bytes: camera (-5, 0, -10*(n/2)+5), focal 1,
+    rotation = calculate_quaternion((0.1, 0, 1)), viewport (2*W/H, 2)."""
+    import struct
+    vw, vh = F(view_width), F(view_height)
+    viewport_h = F(2.0)
+    viewport_w = F(viewport_h * F(vw / vh))
+    q = calculate_quaternion((0.1, 0.0, 1.0))
+    center = (F(-5.0), F(0.0), F(F(F(-10.0) * F(F(maze_n) / F(2.0))) + F(5.0)))
+    return struct.pack("<3f f 4f 2f 2f 2I", *[float(v) for v in center], 1.0, *[float(v) for v in q], float(viewport_w), float(viewport_h),
+                       float(vw), float(vh), int(chunk_width), int(time))
+
+
+def gen_chunks(view_width, view_height, chunk_width):
+    """gen_pixels without the shuffle (main.rs:293-302): x outer, y inner; (u32, u32) pairs."""
+    w, h = int(view_width) // chunk_width, int(view_height) // chunk_width
+    out = np.zeros((w * h, 2), dtype=np.uint32)
+    out[:, 0] = np.repeat(np.arange(w, dtype=np.uint32) * chunk_width, h)
+    out[:, 1] = np.tile(np.arange(h, dtype=np.uint32) * chunk_width, w)
+    return out

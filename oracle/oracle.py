@@ -50,6 +50,22 @@ def lib():
     return _lib
 
 
+def use_native():
+    """bench.py only: build oracle/_native/libmm_oracle.so on THIS machine (g++ -march=native, same source, still no
+    contraction and no fast-math) and use it for every later call.  Returns a one-line description of what is in use.
+    Must run before the first lib() call of the process."""
+    global _LIB, _lib
+    native = os.path.join(_HERE, "_native", "libmm_oracle.so")
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception as e:
+        return f"portable build (native build failed: {type(e).__name__})"
+    if _lib is not None or not os.path.exists(native):
+        return "portable build"
+    _LIB = native
+    return "g++ -O2 -march=native -ffp-contract=off -fopenmp, built on this machine"
+
+
 def num_threads():
     return int(lib().mmo_num_threads())
 

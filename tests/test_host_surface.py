@@ -204,3 +204,18 @@ def test_rect_edge_thresholds_equal_divide_then_compare(mm):
     assert not _literal_edge_test(x, np.float32(0.0)).any()
     for bad in (1e-30, 2.0 ** -21, 2.0 ** 24, np.inf, np.nan, -1.0, 1e-45):
         assert mm.rect_edge_thresholds(bad) is None
+
+
+def test_reference_arm_inputs_equal_the_products(mm):
+    """bench.py --impl reference builds its workload with oracle/host_ref.py only (no product library mapped): the uniform
+    bytes and the chunk list must be the product's (mm_default_uniform / mm_gen_chunks), and so must the scene arrays."""
+    from oracle import host_ref
+
+    for n, W, H, t in ((32, 1920, 1080, 0), (64, 3840, 2160, 5), (10, 1024, 768, 3), (256, 1920, 1080, 1)):
+        assert bytes(mm.default_uniform(n, W, H, 4, t)) == host_ref.default_uniform_bytes(n, W, H, 4, t)
+        assert mm.gen_chunks(W, H, 4).tobytes() == host_ref.gen_chunks(W, H, 4).tobytes()
+    ref, sc = host_ref.build_scene(32, 0), mm.MazeScene(32, 0)
+    assert np.ascontiguousarray(ref["planes"]).tobytes() == np.ascontiguousarray(sc.planes).tobytes()
+    assert np.ascontiguousarray(ref["nodes"]).tobytes() == np.ascontiguousarray(sc.nodes).tobytes()
+    assert np.array_equal(ref["indices"], sc.indices) and np.array_equal(ref["materials"], sc.materials)
+    assert np.ascontiguousarray(ref["emissions"], dtype=np.float32).tobytes() == np.ascontiguousarray(sc.emissions, dtype=np.float32).tobytes()
