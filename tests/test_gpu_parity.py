@@ -660,11 +660,12 @@ def test_multi_gpu_one_process_frame_equals_single_gpu_frame(mm, noise, scenes, 
             m = mm.MultiRenderer(devs, exchange); m.upload_scene(sc, noise)
             hf = mm.HostFrame(int(u.view_height), int(u.view_width))
             m.render(u, q, ch, hf)
+            import ctypes as C
+            cudart = C.CDLL("libcudart.so.12")                          # the runtime torch already loaded
+            cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
             for i, d in enumerate(devs):
                 t = torch.empty((int(u.view_height), int(u.view_width), 4), dtype=torch.float32, device=f"cuda:{d}")
-                with torch.cuda.device(d):
-                    import ctypes as C
-                    cudart = torch.cuda.cudart()
-                    assert int(cudart.cudaMemcpy(t.data_ptr(), m.frame_device_ptr(i), t.numel() * 4, 3)) == 0   # cudaMemcpyDeviceToDevice
+                torch.cuda.synchronize(d)
+                assert cudart.cudaMemcpy(t.data_ptr(), m.frame_device_ptr(i), t.numel() * 4, 4) == 0          # cudaMemcpyDefault
                 assert t.cpu().numpy().tobytes() == full.tobytes(), (exchange, d)
             m.close(); hf.close()
