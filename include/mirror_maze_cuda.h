@@ -80,6 +80,10 @@ typedef struct mm_params {
 
 #define MM_FLAG_COUNTERS      1u   /* fill mm_counters beyond `rays` (slower kernel variant)          */
 #define MM_FLAG_FORCE_LITERAL 2u   /* use the literal-divide traversal for every ray (validation)     */
+#define MM_FLAG_POOL_KERNEL  256u   /* trace with the persistent ray-pool kernel (pool_kernel.cu: warps own a pool of paths in shared
+                                      memory and run interior / leaf / shade bodies on work queues) instead of the default
+                                      one-thread-per-path kernel (render_kernel.cu).  Same bits; measured slower on B200
+                                      (profiles/r2_pool_kernel.md), kept as the evidence for that design                    */
 #define MM_FLAG_NO_ZERO_COPY 128u  /* mm_render / mm_render_async: copy the screen with a DMA transfer even when out_rgba is mapped pinned
                                       memory the kernel could store into directly (for comparisons)                        */
 #define MM_FLAG_RCP_SLAB     64u   /* opt-in arithmetic variant: slab quotients (b - o) * RN(1/d) instead of the literal

@@ -15,6 +15,7 @@ FLAG_COUNTERS = 1
 FLAG_FORCE_LITERAL = 2
 FLAG_RCP_SLAB = 64
 FLAG_NO_ZERO_COPY = 128
+FLAG_POOL_KERNEL = 256
 EXCHANGE_PEER, EXCHANGE_NCCL, EXCHANGE_NONE = 0, 1, 2
 MAX_PEERS = 8
 

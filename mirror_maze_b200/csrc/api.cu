@@ -191,6 +191,47 @@ int mm_set_chunks(mm_ctx *ctx, const mm_chunk *chunks, uint32_t n_chunks) {
 
 namespace mmapi {
 
+static uint32_t env_u32(const char *name, uint32_t dflt, uint32_t lo, uint32_t hi) {
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    const long x = strtol(v, nullptr, 10);
+    return x < (long)lo ? lo : (x > (long)hi ? hi : (uint32_t)x);
+}
+
+// The persistent ray-pool kernel (pool_kernel.cu; opt-in: MM_FLAG_POOL_KERNEL, or MM_KERNEL=pool in the environment for
+// tuning runs) covers the common arithmetic mode: exact shared-reciprocal slab quotients, divide-free rect edge tests,
+// spp <= 64.  Everything else (MM_FLAG_FORCE_LITERAL, MM_FLAG_RCP_SLAB, scenes outside the guarded coordinate / edge-length
+// ranges, spp > 64) runs the default one-thread-per-path kernel whatever the flag says.  Geometry of a warp's
+// pool: M path records of (24 + stack) words, five 128-byte ring queues, R pixel records of (4 + 3 spp) words.
+// MM_POOL_M / MM_POOL_WARPS / MM_POOL_BLOCKS / MM_POOL_TH are developer overrides for tuning runs.
+static bool configure_pool(mm_ctx *ctx, const mm_params *par, Launch &L) {
+    KParams &p = L.p;
+    const char *env_kernel = getenv("MM_KERNEL");
+    const bool want = (par->flags & MM_FLAG_POOL_KERNEL) || (env_kernel && !strcmp(env_kernel, "pool"));
+    if (!want || p.force_literal || p.rcp_mode || !p.scene_fast_ok || !p.rect_fast_ok ||
+        p.spp > 64 || p.total_paths >= 0xFFFF0000ull || ctx->depth > 200)
+        return false;
+    const uint32_t stack_words = ((ctx->depth > 4 ? ctx->depth : 4) + 3u) & ~3u;     // occupancy <= depth - 1, plus the sentinel
+    const uint32_t warps = env_u32("MM_POOL_WARPS", 1, 1, 4);
+    uint32_t M = env_u32("MM_POOL_M", 96, 32, 128);
+    const uint32_t SW = 24 + stack_words;
+    uint32_t R = 0, region = 0;
+    for (;; M -= 8) {                                                             // shrink the pool until the block fits the SM's shared memory
+        R = (M + p.spp - 1) / p.spp + (32 + p.spp - 1) / p.spp + 3;
+        region = (M * SW + 5 * 128 / 4 + R * (4 + 3 * p.spp) + 3u) & ~3u;
+        if ((size_t)region * 4 * warps <= ctx->smem_optin || M <= 32) break;
+    }
+    if ((size_t)region * 4 * warps > ctx->smem_optin || R > 255) return false;
+    p.pool_M = M; p.pool_slot_words = SW; p.pool_R = R; p.pool_region_words = region;
+    p.pool_th_leaf = env_u32("MM_POOL_TH_LEAF", env_u32("MM_POOL_TH", 24, 1, 32), 1, 32);
+    p.pool_th_shade = env_u32("MM_POOL_TH_SHADE", env_u32("MM_POOL_TH", 24, 1, 32), 1, 32);
+    L.choice.pool = true;
+    L.choice.block_threads = (int)(32 * warps);
+    L.smem = (size_t)region * 4 * warps;
+    L.blocks = 0;                                                                  // persistent grid: sized in do_launch from the occupancy query
+    return true;
+}
+
 int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool debug, Launch &L) {
     if (!uni || !par) return fail(ctx, MM_ERR_INVALID, "null uniform or params");
     if (!ctx->have_scene) return fail(ctx, MM_ERR_NO_SCENE, "no scene uploaded");
@@ -238,6 +279,8 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
 
     L.choice.debug = debug;
     L.choice.counters = debug || (par->flags & MM_FLAG_COUNTERS);
+    L.choice.pool = false;
+    if (configure_pool(ctx, par, L)) return MM_OK;
     const int bt = block_threads_for(p.spp);
     L.choice.block_threads = bt;
     L.smem = 3 * (size_t)bt * sizeof(float);                             // reduction scratch
@@ -248,7 +291,7 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
 }
 
 int do_launch(mm_ctx *ctx, Launch &L) {
-    const void *fn = kernel_ptr(L.choice);
+    const void *fn = L.choice.pool ? pool_kernel_ptr(L.choice) : kernel_ptr(L.choice);
     if (fn != ctx->cfg_fn || L.smem != ctx->cfg_smem) {   // once per kernel variant, not per frame
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
         int per_sm = 0;
@@ -259,7 +302,18 @@ int do_launch(mm_ctx *ctx, Launch &L) {
     ctx->last_smem = (uint32_t)L.smem; ctx->last_block_threads = (uint32_t)L.choice.block_threads;
     CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    CK(launch_trace(L.p, L.choice, L.blocks, L.smem, ctx->stream));
+    if (L.choice.pool) {
+        uint32_t per_sm = ctx->last_blocks_per_sm ? ctx->last_blocks_per_sm : 1u;
+        const uint32_t cap = env_u32("MM_POOL_BLOCKS", 0, 0, 64);
+        if (cap && cap < per_sm) per_sm = cap;
+        const uint64_t unit = L.p.spp > 32 ? L.p.spp : 32, units = (L.p.total_paths + unit - 1) / unit;
+        uint64_t blocks = (uint64_t)ctx->n_sms * per_sm;
+        const uint64_t want = (units + (uint64_t)(L.choice.block_threads / 32) - 1) / (uint64_t)(L.choice.block_threads / 32);
+        if (blocks > want) blocks = want ? want : 1;                                 // tiny dispatches: no more warps than units
+        CK(launch_pool(L.p, L.choice, (unsigned)blocks, (unsigned)L.choice.block_threads, L.smem, ctx->stream));
+    } else {
+        CK(launch_trace(L.p, L.choice, L.blocks, L.smem, ctx->stream));
+    }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaEventRecord(ctx->ev2, ctx->stream));      // mm_last_counters waits on this, not on the whole stream

@@ -48,6 +48,7 @@ struct __align__(16) RectS {
 
 struct Counters {   // device-side mirror of mm_counters
     unsigned long long paths, rays, inner_visits, leaf_visits, rect_tests, hits, literal_rays, max_stack;
+    unsigned long long next_unit;   // pool kernel: work-distribution ticket (zeroed with the counters before every launch)
 };
 
 struct KParams {
@@ -79,6 +80,12 @@ struct KParams {
     uint32_t n_peers;
     uint32_t peers_multicast;  // peers[0] is an NVSwitch multicast address: stored with multimem.st, the only defined access to one
     float *host_out;           // mapped pinned host frame every finished pixel is also stored into (zero-copy output); may be null
+    // pool kernel (pool_kernel.cu): per-warp pool geometry in shared memory
+    uint32_t pool_M;            // path records per warp (<= 128)
+    uint32_t pool_slot_words;   // record stride in words: 24 + traversal stack (BVH depth rounded up to 4)
+    uint32_t pool_R;            // pixel records per warp
+    uint32_t pool_region_words; // words of shared memory per warp
+    uint32_t pool_th_leaf, pool_th_shade;   // a body below 32 ready paths runs once this many wait for it
     Counters *counters;
     uint32_t *dbg_first_hit, *dbg_segments, *dbg_mirror_hits;
     float *dbg_radiance;
@@ -95,8 +102,10 @@ constexpr int kLargeBlock = 256;
 inline int block_threads_for(uint32_t spp) { return spp <= (uint32_t)kSmallBlock ? kSmallBlock : kLargeBlock; }
 
 // Returns the kernel's static properties for the occupancy query and launch.
-struct KernelChoice { bool counters, debug; int block_threads; };
+struct KernelChoice { bool counters, debug; int block_threads; bool pool; };
 const void *kernel_ptr(KernelChoice c);
+const void *pool_kernel_ptr(KernelChoice c);
+cudaError_t launch_pool(const KParams &p, KernelChoice c, unsigned blocks, unsigned threads, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_trace(const KParams &p, KernelChoice c, unsigned blocks, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_mb_gather(const void *table, uint32_t n_records, uint32_t iters, unsigned blocks, float *sink, cudaStream_t stream);
 cudaError_t launch_mb_ffma(uint32_t iters, unsigned blocks, float *sink, cudaStream_t stream);

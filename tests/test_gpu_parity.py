@@ -669,3 +669,26 @@ def test_multi_gpu_one_process_frame_equals_single_gpu_frame(mm, noise, scenes, 
                 assert cudart.cudaMemcpy(t.data_ptr(), m.frame_device_ptr(i), t.numel() * 4, 4) == 0          # cudaMemcpyDefault
                 assert t.cpu().numpy().tobytes() == full.tobytes(), (exchange, d)
             m.close(); hf.close()
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2_small", "cfg3_small", "maze64", "maze256", "ref_dispatch", "yaw", "tiny_origin", "on_plane",
+                                  "mirror_limit2", "bounce0", "bounce1", "all_miss", "ragged", "chunk2_spp4", "chunk5_spp32", "chunk16_spp1",
+                                  "chunk8_spp2", "chunk3_spp32"])
+def test_pool_kernel_matches_oracle(mm, oracle, noise, scenes, renderer, name):
+    """MM_FLAG_POOL_KERNEL: the persistent ray-pool kernel (pool_kernel.cu) — warps that own a pool of paths in shared memory
+    and run generate / interior / leaf / shade bodies from work queues — gives every observable and counter of the oracle,
+    including rays that take the literal-divide traversal (tiny_origin), paths that end at once (bounce0), 1 to 64 samples per
+    pixel, ragged frames and thread groups that straddle warps (chunk5_spp32)."""
+    sc, u, p, ch = build_case(mm, name, scenes)
+    renderer.upload_scene(sc, noise)
+    ref = oracle.render(sc, noise, u, p, ch, debug=True)
+    p.flags = mm.FLAG_POOL_KERNEL
+    assert_same(renderer.render(u, p, ch, debug=True), ref)
+    p.flags = mm.FLAG_POOL_KERNEL | mm.FLAG_COUNTERS
+    img, cnt, _ = renderer.render(u, p, ch)
+    assert img.tobytes() == ref[0].tobytes()
+    for k in COUNTER_KEYS:
+        assert cnt[k] == ref[1][k], k
+    p.flags = mm.FLAG_POOL_KERNEL
+    img, cnt, _ = renderer.render(u, p, ch)
+    assert img.tobytes() == ref[0].tobytes() and cnt["rays"] == ref[1]["rays"] and cnt["hits"] == ref[1]["hits"]
