@@ -120,3 +120,28 @@ def test_packed_fp32_instruction_mix_shows_no_contraction():
     sass = subprocess.run([tool, "-sass", obj], capture_output=True, text=True, check=True).stdout
     n_add, n_mul, n_fma = (sass.count(f" {op} ") for op in ("FADD2", "FMUL2", "FFMA2"))
     assert n_add > 0 and n_add == n_mul and 2 * n_fma == 3 * n_mul, (n_add, n_mul, n_fma)
+
+
+def test_new_entry_points_fail_cleanly_without_a_gpu(mm):
+    """mm_multi_create / mm_host_alloc / mm_render_async on a box without a CUDA device: error codes, no crash, no fallback."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = mm.load_library()
+    devs = (C.c_int * 2)(0, 1)
+    h = C.c_void_p()
+    assert lib.mm_multi_create(devs, 2, mm.EXCHANGE_PEER, C.byref(h)) < 0 and not h.value
+    assert b"device" in lib.mm_multi_last_error(None).lower() or lib.mm_multi_last_error(None) != b""
+    assert lib.mm_multi_create(devs, 0, mm.EXCHANGE_PEER, C.byref(h)) == -1
+    assert lib.mm_multi_create(devs, 2, 7, C.byref(h)) == -1
+    dup = (C.c_int * 2)(0, 0)
+    assert lib.mm_multi_create(dup, 2, mm.EXCHANGE_NCCL, C.byref(h)) == -1
+    assert lib.mm_multi_destroy(None) == 0 and lib.mm_multi_n_devices(None) == 0
+    p = C.c_void_p()
+    assert lib.mm_host_alloc(1 << 20, C.byref(p)) < 0 and not p.value
+    assert lib.mm_host_alloc(0, C.byref(p)) == -1
+    assert lib.mm_host_free(None) == 0 and lib.mm_host_unregister(None) == 0
+    assert lib.mm_host_free(C.c_void_p(12345)) == -1               # never allocated here
+    assert lib.mm_render_async(None, None, None, None, 0, None, None) == -1
+    assert lib.mm_wait(None, None) == -1
