@@ -22,7 +22,11 @@ const _: () = assert!(std::mem::size_of::<Plane>() == 48 && std::mem::size_of::<
     && std::mem::size_of::<Camera>() == 40 && std::mem::size_of::<Uniform>() == 56 && std::mem::size_of::<Params>() == 36);
 
 #[repr(C)] pub struct mm_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct mm_multi { _p: [u8; 0] }
 #[repr(C)] pub struct mm_scene { _p: [u8; 0] }
+pub const MM_EXCHANGE_PEER: c_int = 0;
+pub const MM_EXCHANGE_NCCL: c_int = 1;
+pub const MM_EXCHANGE_NONE: c_int = 2;
 
 extern "C" {
     pub fn mm_create(cuda_device: c_int, out: *mut *mut mm_ctx) -> c_int;
@@ -33,6 +37,23 @@ extern "C" {
                            noise_rgba8: *const u8, noise_w: u32, noise_h: u32) -> c_int;
     pub fn mm_render(ctx: *mut mm_ctx, uni: *const Uniform, params: *const Params, chunks: *const Chunk, n_chunks: u32,
                      out_rgba: *mut f32, counters: *mut Counters, debug: *const std::ffi::c_void) -> c_int;
+    // commit() without wait (main.rs:894) / the wait the reference never needs because it presents a drawable
+    pub fn mm_render_async(ctx: *mut mm_ctx, uni: *const Uniform, params: *const Params, chunks: *const Chunk, n_chunks: u32,
+                           out_rgba: *mut f32, debug: *const std::ffi::c_void) -> c_int;
+    pub fn mm_wait(ctx: *mut mm_ctx, counters: *mut Counters) -> c_int;
+    // pin + map a Vec<f32> frame once: the kernel then stores finished pixels straight into it (zero-copy output)
+    pub fn mm_host_register(ptr: *mut std::ffi::c_void, bytes: usize) -> c_int;
+    pub fn mm_host_unregister(ptr: *mut std::ffi::c_void) -> c_int;
+    // one process, several GPUs
+    pub fn mm_multi_create(devices: *const c_int, n: c_int, exchange: c_int, out: *mut *mut mm_multi) -> c_int;
+    pub fn mm_multi_destroy(m: *mut mm_multi) -> c_int;
+    pub fn mm_multi_last_error(m: *const mm_multi) -> *const c_char;
+    pub fn mm_multi_upload_scene(m: *mut mm_multi, planes: *const Plane, n_planes: u32, nodes: *const BVHNode, n_nodes: u32,
+                                 indices: *const u32, materials: *const u8, emissions: *const Float4,
+                                 noise_rgba8: *const u8, noise_w: u32, noise_h: u32) -> c_int;
+    pub fn mm_multi_render(m: *mut mm_multi, uni: *const Uniform, params: *const Params, chunks: *const Chunk, n_chunks: u32,
+                           out_rgba: *mut f32, counters: *mut Counters) -> c_int;
+    pub fn mm_multi_last_ms(m: *mut mm_multi, ms: *mut f32) -> c_int;
     pub fn mm_present(ctx: *mut mm_ctx, out_rgba: *mut f32) -> c_int;
     pub fn mm_last_ms(ctx: *mut mm_ctx, ms: *mut f32) -> c_int;
     pub fn mm_scene_build(maze_n: u32, seed: u64, fast_bvh: c_int, out: *mut *mut mm_scene) -> c_int;
