@@ -80,6 +80,11 @@ typedef struct mm_params {
 
 #define MM_FLAG_COUNTERS      1u   /* fill mm_counters beyond `rays` (slower kernel variant)          */
 #define MM_FLAG_FORCE_LITERAL 2u   /* use the literal-divide traversal for every ray (validation)     */
+#define MM_FLAG_SCREEN_RGBA8 512u   /* the screen is an RGBA8Unorm texture, as the reference's is (main.rs:702-709): every pixel the dispatch
+                                      stores is quantised per channel to rte(clamp(v, 0, 1) * 255) / 255 — what a read of the RGBA8Unorm
+                                      texel returns (Metal's float -> unorm8 conversion rounds to nearest even) — so the persistent
+                                      screen, the blur that feeds on it (mm_present_rgba8) and the frame hold 8-bit values.  Default is
+                                      the unquantised fp32 screen the 1e-3 radiance tolerance is stated on.                       */
 #define MM_FLAG_POOL_KERNEL  256u   /* trace with the persistent ray-pool kernel (pool_kernel.cu: warps own a pool of paths in shared
                                       memory and run interior / leaf / shade bodies on work queues) instead of the default
                                       one-thread-per-path kernel (render_kernel.cu).  Same bits; measured slower on B200
@@ -258,6 +263,10 @@ int mm_get_scene_info(mm_ctx *ctx, mm_scene_info *out);
  * mm_present_blur_device is the same kernel on caller device buffers (src != dst), asynchronous.
  */
 int mm_present(mm_ctx *ctx, float *out_rgba);
+/* The present pass on an RGBA8Unorm screen (use with MM_FLAG_SCREEN_RGBA8 dispatches): the blur's result is written back
+ * quantised, like fragment_shader's store into the 8-bit drawable / screen texture.  out_rgba (H*W*4 floats, values k/255) and
+ * out_rgba8 (H*W*4 bytes, the texels themselves) may each be null.  Synchronous. */
+int mm_present_rgba8(mm_ctx *ctx, float *out_rgba, uint8_t *out_rgba8);
 int mm_present_blur_device(mm_ctx *ctx, const float *d_src, float *d_dst, uint32_t width, uint32_t height);
 
 /*

@@ -16,6 +16,7 @@ FLAG_FORCE_LITERAL = 2
 FLAG_RCP_SLAB = 64
 FLAG_NO_ZERO_COPY = 128
 FLAG_POOL_KERNEL = 256
+FLAG_SCREEN_RGBA8 = 512
 EXCHANGE_PEER, EXCHANGE_NCCL, EXCHANGE_NONE = 0, 1, 2
 MAX_PEERS = 8
 
@@ -138,6 +139,7 @@ PROTOTYPES = {
     "mm_rect_edge_thresholds": (C.c_int, [C.c_float, _P(C.c_float), _P(C.c_float)]),
     "mm_microbench": (C.c_int, [_vp, C.c_int, C.c_uint64, _P(C.c_double)]),
     "mm_present": (C.c_int, [_vp, _vp]),
+    "mm_present_rgba8": (C.c_int, [_vp, _vp, _vp]),
     "mm_present_blur_device": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32]),
     "mm_move_camera": (C.c_int, [_vp, C.c_uint32, Float3, Float4, _vp, C.c_uint32, C.c_float, _P(Float3)]),
     "mm_bag_new": (C.c_int, [C.c_float, C.c_float, C.c_uint32, C.c_uint64, _P(_vp)]),

@@ -271,6 +271,7 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
     p.force_literal = (par->flags & MM_FLAG_FORCE_LITERAL) ? 1u : 0u;
     p.rcp_mode = (par->flags & MM_FLAG_RCP_SLAB) ? 1u : 0u;
     p.scene_fast_ok = ctx->fast_ok ? 1u : 0u;
+    p.quant8 = (par->flags & MM_FLAG_SCREEN_RGBA8) ? 1u : 0u;
     p.rect_fast_ok = (ctx->rect_fast_ok && !(par->flags & MM_FLAG_FORCE_LITERAL)) ? 1u : 0u;
     p.total_paths = (uint64_t)count * T;
     p.pairs = ctx->d_pairs; p.rects = ctx->d_rects; p.shade = ctx->d_shade;
@@ -326,7 +327,8 @@ int ensure_screen(mm_ctx *ctx, uint32_t W, uint32_t H) {
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->d_screen);
     cudaFree(ctx->d_screen2);
-    ctx->d_screen = nullptr; ctx->d_screen2 = nullptr;
+    cudaFree(ctx->d_screen8);
+    ctx->d_screen = nullptr; ctx->d_screen2 = nullptr; ctx->d_screen8 = nullptr;
     CK(cudaMalloc(&ctx->d_screen, (size_t)W * H * 4 * sizeof(float)));
     CK(cudaMemsetAsync(ctx->d_screen, 0, (size_t)W * H * 4 * sizeof(float), ctx->stream));
     ctx->screen_w = W; ctx->screen_h = H;
@@ -582,19 +584,23 @@ int mm_present_blur_device(mm_ctx *ctx, const float *d_src, float *d_dst, uint32
     return MM_OK;
 }
 
-int mm_present(mm_ctx *ctx, float *out_rgba) {
+static int present_impl(mm_ctx *ctx, float *out_rgba, bool q8, uint8_t *out_rgba8) {
     if (!ctx) return MM_ERR_INVALID;
     ctx->err.clear();
     if (!ctx->d_screen) return fail(ctx, MM_ERR_INVALID, "mm_present: nothing rendered yet");
     CK(cudaSetDevice(ctx->device));
-    const size_t bytes = (size_t)ctx->screen_w * ctx->screen_h * 4 * sizeof(float);
+    const size_t n_px = (size_t)ctx->screen_w * ctx->screen_h, bytes = n_px * 4 * sizeof(float);
     if (!ctx->d_screen2) CK(cudaMalloc(&ctx->d_screen2, bytes));
-    CK(launch_blur(ctx->d_screen, ctx->d_screen2, ctx->screen_w, ctx->screen_h, ctx->stream));
+    if (out_rgba8 && !ctx->d_screen8) CK(cudaMalloc(&ctx->d_screen8, n_px * 4));
+    CK(launch_blur(ctx->d_screen, ctx->d_screen2, ctx->screen_w, ctx->screen_h, ctx->stream, q8, out_rgba8 ? ctx->d_screen8 : nullptr));
     float *t = ctx->d_screen; ctx->d_screen = ctx->d_screen2; ctx->d_screen2 = t;   // the blurred image is the screen now
     if (out_rgba) CK(cudaMemcpyAsync(out_rgba, ctx->d_screen, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_rgba8) CK(cudaMemcpyAsync(out_rgba8, ctx->d_screen8, n_px * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return MM_OK;
 }
+int mm_present(mm_ctx *ctx, float *out_rgba) { return present_impl(ctx, out_rgba, false, nullptr); }
+int mm_present_rgba8(mm_ctx *ctx, float *out_rgba, uint8_t *out_rgba8) { return present_impl(ctx, out_rgba, true, out_rgba8); }
 
 int mm_microbench(mm_ctx *ctx, int kind, uint64_t table_bytes, double *result) {
     if (!ctx || !result) return MM_ERR_INVALID;

@@ -105,8 +105,9 @@ __global__ void __launch_bounds__(128) pool_kernel(const __grid_constant__ KPara
         if (last) {
             const float *sm = reinterpret_cast<const float *>(rec + kPrecHdr);
             const float d = (float)(int)spp;
-            const float4 px = make_float4(fdiv(reduce_samples(sm, spp, 1), d), fdiv(reduce_samples(sm + spp, spp, 1), d),
-                                          fdiv(reduce_samples(sm + 2 * spp, spp, 1), d), 1.0f);
+            float4 px = make_float4(fdiv(reduce_samples(sm, spp, 1), d), fdiv(reduce_samples(sm + spp, spp, 1), d),
+                                    fdiv(reduce_samples(sm + 2 * spp, spp, 1), d), 1.0f);
+            if (P.quant8) px = quant8(px);
             const uint32_t pxx = rec[1], pxy = rec[2];
             if (P.tiles) reinterpret_cast<float4 *>(P.tiles)[rec[3]] = px;
             if (pxx < P.W && pxy < P.H) {

@@ -116,7 +116,8 @@ trace_kernel(const __grid_constant__ KParams P) {
             sx = fadd(sx, rx[tid + 8 * i]); sy = fadd(sy, ry[tid + 8 * i]); sz = fadd(sz, rz[tid + 8 * i]);
         }
         const float d = (float)(int)P.spp;
-        const float4 px = make_float4(fdiv(sx, d), fdiv(sy, d), fdiv(sz, d), 1.0f);
+        float4 px = make_float4(fdiv(sx, d), fdiv(sy, d), fdiv(sz, d), 1.0f);
+        if (P.quant8) px = quant8(px);
         if (P.image && pxx < P.W && pxy < P.H) reinterpret_cast<float4 *>(P.image)[(size_t)pxy * P.W + pxx] = px;
         if (P.tiles) reinterpret_cast<float4 *>(P.tiles)[(size_t)k * P.ppc + (flat >> P.log2_spp)] = px;
         if ((P.n_peers || P.host_out) && pxx < P.W && pxy < P.H) {
@@ -239,7 +240,8 @@ __global__ void quot_selftest_kernel(uint64_t n, uint64_t seed, unsigned long lo
 
 // fragment_shader's 5-tap blur (shaders.metal:214-225), ping-pong: one thread per pixel, one float4 per tap.  HBM-bound:
 // 16 B read + 16 B written per pixel (the four neighbour taps hit L1/L2).
-__global__ void __launch_bounds__(256) blur_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, uint32_t W, uint32_t H) {
+__global__ void __launch_bounds__(256) blur_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, uint32_t W, uint32_t H, bool q8,
+                                                   uchar4 *__restrict__ bytes) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W || y >= H) return;
     const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -252,7 +254,9 @@ __global__ void __launch_bounds__(256) blur_kernel(const float4 *__restrict__ sr
     o.y = fdiv(fadd(fadd(c.y, fdiv(fadd(r.y, l.y), 2.0f)), fdiv(fadd(d.y, u.y), 2.0f)), 3.0f);
     o.z = fdiv(fadd(fadd(c.z, fdiv(fadd(r.z, l.z), 2.0f)), fdiv(fadd(d.z, u.z), 2.0f)), 3.0f);
     o.w = 1.0f;
+    if (q8) o = quant8(o);
     dst[row + x] = o;
+    if (bytes) bytes[row + x] = make_uchar4((unsigned char)unorm8(o.x), (unsigned char)unorm8(o.y), (unsigned char)unorm8(o.z), (unsigned char)unorm8(o.w));
 }
 
 // Micro-benchmarks for the two rooflines the path is measured against (SURVEY §8 d): how fast can this GPU fetch 56 useful
@@ -323,10 +327,11 @@ cudaError_t launch_scatter_all(const float *gathered, float *image, const mm_chu
     return cudaGetLastError();
 }
 
-cudaError_t launch_blur(const float *src, float *dst, uint32_t W, uint32_t H, cudaStream_t stream) {
+cudaError_t launch_blur(const float *src, float *dst, uint32_t W, uint32_t H, cudaStream_t stream, bool quant8, uint8_t *bytes) {
     if (W == 0 || H == 0) return cudaSuccess;
     dim3 grid((W + 255) / 256, H);
-    blur_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), W, H);
+    blur_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), W, H, quant8,
+                                          reinterpret_cast<uchar4 *>(bytes));
     return cudaGetLastError();
 }
 

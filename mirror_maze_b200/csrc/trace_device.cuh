@@ -433,6 +433,11 @@ __device__ __forceinline__ bool ray_is_literal(const KParams &P, V3 ori, V3 dir)
                         : (axis_safe(ori.x, dir.x) && axis_safe(ori.y, dir.y) && axis_safe(ori.z, dir.z)));
 }
 
+// Store into an RGBA8Unorm texture and read back (main.rs:702-709): rte(clamp(v, 0, 1) * 255) / 255; NaN stores 0.
+__device__ __forceinline__ uint32_t unorm8(float v) { return min(__float2uint_rn(fmul(fminf(fmaxf(v, 0.0f), 1.0f), 255.0f)), 255u); }
+__device__ __forceinline__ float quant8(float v) { return fdiv(__uint2float_rn(unorm8(v)), 255.0f); }
+__device__ __forceinline__ float4 quant8(float4 p) { return make_float4(quant8(p.x), quant8(p.y), quant8(p.z), quant8(p.w)); }
+
 // Per-pixel reduction of spp tone-mapped samples in the reference's order (shaders.metal:343-364): pairs, quads, octets (the
 // phases whose stride is < spp), then the octets serially.  v[i * stride] is sample i.
 __device__ __forceinline__ float reduce_samples(const float *v, uint32_t spp, uint32_t stride) {

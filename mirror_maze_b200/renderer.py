@@ -198,6 +198,13 @@ class Renderer:
         self._ck(self._lib.mm_present(self._ctx, out.ctypes.data if copy else None))
         return out
 
+    def present_rgba8(self, out=None, out_bytes=None):
+        """mm_present_rgba8: the present blur on an RGBA8Unorm screen; fills the float frame (values k/255) and / or the
+        uint8 [H, W, 4] texel array."""
+        self._ck(self._lib.mm_present_rgba8(self._ctx, None if out is None else out.ctypes.data,
+                                            None if out_bytes is None else out_bytes.ctypes.data))
+        return out, out_bytes
+
     def present_blur_device(self, src_ptr, dst_ptr, width, height):
         self._ck(self._lib.mm_present_blur_device(self._ctx, src_ptr, dst_ptr, width, height))
 

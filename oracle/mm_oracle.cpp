@@ -46,6 +46,13 @@ struct f3 { float x, y, z; };
 inline f3 mk(float x, float y, float z) { f3 r = {x, y, z}; return r; }
 inline f3 ld(const mm_float3 &a) { return mk(a.x, a.y, a.z); }
 inline f3 add(f3 a, f3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+// Store into an RGBA8Unorm texture and read back (reference src/main.rs:702-709 creates the screen as RGBA8Unorm): Metal converts
+// float -> unorm8 as round-to-nearest-even of clamp(v, 0, 1) * 255 (NaN -> 0) and unorm8 -> float as k / 255.
+inline float quant8(float v) {
+    float c = v > 0.0f ? v : 0.0f;                 // also maps NaN to 0
+    c = c < 1.0f ? c : 1.0f;
+    return std::nearbyintf(c * 255.0f) / 255.0f;   // default rounding mode: to nearest even
+}
 inline f3 sub(f3 a, f3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
 inline f3 mul(f3 a, f3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
 inline f3 scale(f3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
@@ -387,10 +394,15 @@ int mmo_render(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *nod
                 for (uint32_t i = 1; i < spp / 8; i++) test[base] = add(test[base], test[base + 8 * i]);
                 float d = (float)(int)spp;
                 f3 r = mk(test[base].x / d, test[base].y / d, test[base].z / d);
+                float alpha = 1.0f;
+                if (params->flags & MM_FLAG_SCREEN_RGBA8) {   // main.rs:702-709: the screen is RGBA8Unorm; a store quantises, a read returns k / 255
+                    r = mk(quant8(r.x), quant8(r.y), quant8(r.z));
+                    alpha = quant8(alpha);
+                }
                 uint32_t x = pix[2 * (size_t)base], y = pix[2 * (size_t)base + 1];
                 if (x < W && y < H) {
                     float *o = out_rgba + 4 * ((size_t)y * W + x);
-                    o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = 1.0f;
+                    o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = alpha;
                 }
             }
         }

@@ -337,7 +337,15 @@ def _render(sc, noise, U_, P, chunks):
     return image, counters, debug
 
 
-def present_blur(img):
+def quant8(a):
+    """Store into an RGBA8Unorm texture and read back: rte(clamp(v, 0, 1) * 255) / 255 in float32, NaN -> 0."""
+    a = np.asarray(a, dtype=F)
+    c = np.where(a > 0, a, F(0.0)).astype(F)
+    c = np.where(c < 1, c, F(1.0)).astype(F)
+    return (np.rint(c * F(255.0)).astype(F) / F(255.0)).astype(F)
+
+
+def present_blur(img, rgba8=False):
     """fragment_shader (reference src/shaders.metal:214-225) as a race-free ping-pong pass over an [H,W,4] float32 image:
     c = img[p]; c += (img[p+(1,0)] + img[p-(1,0)]) / 2; c += (img[p+(0,1)] + img[p-(0,1)]) / 2; c /= 3; out = (c.rgb, 1).
     Reads outside the texture return 0."""
@@ -351,4 +359,4 @@ def present_blur(img):
     o = (c + (r + l) / F(2.0)) + (d + u) / F(2.0)
     o = o / F(3.0)
     o[..., 3] = F(1.0)
-    return o.astype(F)
+    return quant8(o) if rgba8 else o.astype(F)

@@ -104,3 +104,56 @@ def test_progressive_refresh_frame_loop(mm, oracle, noise, scenes):
         screen = np_oracle.present_blur(screen)
         assert out.tobytes() == screen.tobytes(), f"frame {frame}"
     r.close()
+
+
+def test_rgba8_screen_quantisation_model(mm, oracle, noise, scenes):
+    """MM_FLAG_SCREEN_RGBA8 (the reference's screen is RGBA8Unorm, main.rs:702-709): the oracle's stored pixels are the fp32
+    frame pushed through rte(clamp(v) * 255) / 255, i.e. exact 8-bit values; the blur model quantises its output the same way."""
+    from cases import build_case
+    from oracle import np_oracle
+
+    sc, u, p, ch = build_case(mm, "yaw", scenes)
+    plain = oracle.render(sc, noise, u, p, ch)[0]
+    p.flags = mm.FLAG_SCREEN_RGBA8
+    q = oracle.render(sc, noise, u, p, ch)[0]
+    assert q.tobytes() == np_oracle.quant8(plain).tobytes()
+    k = q * np.float32(255.0)
+    assert np.array_equal(np.rint(k), k.round(3)) and q.min() >= 0 and q.max() <= 1          # values are k / 255
+    assert np_oracle.quant8(np.array([np.nan, -1.0, 0.5, 2.0, 0.5 / 255, 1.5 / 255], np.float32)).tolist() == \
+        [0.0, 0.0, float(np.float32(128.0) / np.float32(255.0)), 1.0, 0.0, float(np.float32(2.0) / np.float32(255.0))]   # ties to even
+    b = np_oracle.present_blur(q, rgba8=True)
+    assert b.tobytes() == np_oracle.quant8(np_oracle.present_blur(q)).tobytes()
+
+
+@pytest.mark.gpu
+def test_rgba8_screen_mode_matches_oracle_and_blur_model(mm, oracle, noise, scenes):
+    """The CUDA path with an RGBA8Unorm screen: dispatch == oracle under the same flag; two frames of progressive refresh + the
+    quantising present blur == oracle + model; the byte frame is the texels."""
+    from cases import build_case
+    from oracle import np_oracle
+
+    sc, u, p, ch = build_case(mm, "yaw", scenes)
+    H, W = int(u.view_height), int(u.view_width)
+    r = mm.Renderer(0)
+    r.upload_scene(sc, noise)
+    for flags in (mm.FLAG_SCREEN_RGBA8, mm.FLAG_SCREEN_RGBA8 | mm.FLAG_POOL_KERNEL):
+        p.flags = flags
+        q = mm.Params.from_buffer_copy(bytes(p)); q.flags = mm.FLAG_SCREEN_RGBA8
+        assert r.render(u, p, ch)[0].tobytes() == oracle.render(sc, noise, u, q, ch)[0].tobytes()
+    r.close()
+    r = mm.Renderer(0)
+    r.upload_scene(sc, noise)
+    screen = np.zeros((H, W, 4), dtype=np.float32)
+    half = mm.Params.from_buffer_copy(bytes(p)); half.flags = mm.FLAG_SCREEN_RGBA8
+    n = p.grid_x * p.grid_y
+    for frame in range(2):
+        half.group_first, half.group_step, half.group_count = frame, 2, (n + 1 - frame) // 2
+        u.time = frame
+        r.render(u, half, ch)
+        oracle.render(sc, noise, u, half, ch, out=screen)
+        out, out8 = np.empty((H, W, 4), np.float32), np.empty((H, W, 4), np.uint8)
+        r.present_rgba8(out, out8)
+        screen = np_oracle.present_blur(screen, rgba8=True)
+        assert out.tobytes() == screen.tobytes()
+        assert np.array_equal(out8, np.rint(screen * np.float32(255.0)).astype(np.uint8))
+    r.close()
