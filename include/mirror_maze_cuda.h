@@ -85,6 +85,10 @@ typedef struct mm_params {
                                       texel returns (Metal's float -> unorm8 conversion rounds to nearest even) — so the persistent
                                       screen, the blur that feeds on it (mm_present_rgba8) and the frame hold 8-bit values.  Default is
                                       the unquantised fp32 screen the 1e-3 radiance tolerance is stated on.                       */
+#define MM_FLAG_REGROUP     1024u   /* trace with trace_kernel_rg: the default kernel plus warp-level ray compaction — at segment boundaries
+                                      the block's live paths are re-formed into warps through shared memory, sorted by ray steepness
+                                      |dir.y|, ended paths dropped.  Same bits; fewer instructions (-14 % interior-body executions) but
+                                      measured slower on B200 (profiles/r2_experiments.md), kept as the evidence for that design    */
 #define MM_FLAG_POOL_KERNEL  256u   /* trace with the persistent ray-pool kernel (pool_kernel.cu: warps own a pool of paths in shared
                                       memory and run interior / leaf / shade bodies on work queues) instead of the default
                                       one-thread-per-path kernel (render_kernel.cu).  Same bits; measured slower on B200

@@ -17,6 +17,7 @@ FLAG_RCP_SLAB = 64
 FLAG_NO_ZERO_COPY = 128
 FLAG_POOL_KERNEL = 256
 FLAG_SCREEN_RGBA8 = 512
+FLAG_REGROUP = 1024
 EXCHANGE_PEER, EXCHANGE_NCCL, EXCHANGE_NONE = 0, 1, 2
 MAX_PEERS = 8
 

@@ -281,10 +281,22 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
     L.choice.debug = debug;
     L.choice.counters = debug || (par->flags & MM_FLAG_COUNTERS);
     L.choice.pool = false;
+    L.choice.regroup = false;
     if (configure_pool(ctx, par, L)) return MM_OK;
-    const int bt = block_threads_for(p.spp);
+    // opt-in (MM_FLAG_REGROUP, or MM_KERNEL=regroup for tuning runs): the kernel that re-forms the block's warps at segment boundaries
+    const char *env_kernel = getenv("MM_KERNEL");
+    L.choice.regroup = (par->flags & MM_FLAG_REGROUP) || (env_kernel && !strcmp(env_kernel, "regroup"));
+    int bt = block_threads_for(p.spp);
+    if (L.choice.regroup) {
+        const int want = (int)env_u32("MM_RG_BLOCK", kLargeBlock, 64, kLargeBlock);       // developer override: 64 / 128 / 256
+        bt = want >= 256 ? 256 : (want >= 128 ? 128 : 64);
+        if ((uint32_t)bt < p.spp) bt = kLargeBlock;                                       // a block holds whole pixels
+        const char *m = getenv("MM_RG_MASK");
+        p.rg_mask = m && *m ? (uint32_t)strtoul(m, nullptr, 0) : 0xFFFFFFFFu;
+    }
     L.choice.block_threads = bt;
     L.smem = 3 * (size_t)bt * sizeof(float);                             // reduction scratch
+    if (L.choice.regroup) L.smem += 4 * (size_t)bt * sizeof(float4) + 64 * sizeof(uint32_t);   // path state in flight + bin counters
     const uint64_t blocks = (p.total_paths + (uint64_t)bt - 1) / (uint64_t)bt;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, MM_ERR_UNSUPPORTED, "too many paths for one launch");
     L.blocks = (unsigned)blocks;

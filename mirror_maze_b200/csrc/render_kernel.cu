@@ -24,6 +24,82 @@
 namespace mmk {
 namespace {
 
+// Block epilogue shared by the trace kernels.  On entry red[] holds every thread's tone-mapped sample (3 planes of
+// kBlockThreads floats, indexed by the thread the path started on) and the block has synchronised.
+template <bool CNT, int kBlockThreads>
+__device__ __forceinline__ void block_epilogue(const KParams &P, float *red, bool active, uint32_t flat, uint32_t pxx, uint32_t pxy, uint32_t k,
+                                               uint32_t seg, uint32_t nhits, uint32_t nliteral, Tally tl) {
+    // Per-pixel reduction in the reference's order (shaders.metal:343-366): pairs, quads, octets (the phases whose
+    // stride is < spp), then the pixel's first thread adds the octets serially and divides by spp.
+    const uint32_t tid = threadIdx.x;
+    float *rx = red, *ry = red + kBlockThreads, *rz = red + 2 * kBlockThreads;
+#pragma unroll
+    for (uint32_t stride = 1; stride <= 4; stride *= 2) {
+        if (stride < P.spp && (tid & (2 * stride - 1)) == 0) {
+            rx[tid] = fadd(rx[tid], rx[tid + stride]);
+            ry[tid] = fadd(ry[tid], ry[tid + stride]);
+            rz[tid] = fadd(rz[tid], rz[tid + stride]);
+        }
+        __syncthreads();
+    }
+    if (active && (flat & (P.spp - 1)) == 0) {
+        float sx = rx[tid], sy = ry[tid], sz = rz[tid];
+        for (uint32_t i = 1; i < P.spp / 8; i++) {
+            sx = fadd(sx, rx[tid + 8 * i]); sy = fadd(sy, ry[tid + 8 * i]); sz = fadd(sz, rz[tid + 8 * i]);
+        }
+        const float d = (float)(int)P.spp;
+        float4 px = make_float4(fdiv(sx, d), fdiv(sy, d), fdiv(sz, d), 1.0f);
+        if (P.quant8) px = quant8(px);
+        if (P.image && pxx < P.W && pxy < P.H) reinterpret_cast<float4 *>(P.image)[(size_t)pxy * P.W + pxx] = px;
+        if (P.tiles) reinterpret_cast<float4 *>(P.tiles)[(size_t)k * P.ppc + (flat >> P.log2_spp)] = px;
+        if ((P.n_peers || P.host_out) && pxx < P.W && pxy < P.H) {
+            const size_t at = (size_t)pxy * P.W + pxx;
+            if (P.host_out) reinterpret_cast<float4 *>(P.host_out)[at] = px;        // zero-copy output: mapped pinned host frame, over PCIe
+            if (P.peers_multicast) {                                    // fused exchange, NVSwitch multicast: one store, replicated by the switch
+                float4 *mc = reinterpret_cast<float4 *>(P.peers[0]) + at;
+                asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(px.x), "f"(px.y), "f"(px.z), "f"(px.w) : "memory");
+            } else {                                                    // fused exchange, NVLink peer mappings: one store per rank's frame
+                for (uint32_t i = 0; i < P.n_peers; i++) reinterpret_cast<float4 *>(P.peers[i])[at] = px;
+            }
+        }
+    }
+
+    // Event counts: warp-reduce, one atomic per warp and counter.
+    {
+        unsigned long long v_rays = seg, v_hits = nhits, v_lit = nliteral, v_paths = active ? 1u : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v_rays += __shfl_xor_sync(0xFFFFFFFFu, v_rays, o);
+            v_hits += __shfl_xor_sync(0xFFFFFFFFu, v_hits, o);
+            v_lit += __shfl_xor_sync(0xFFFFFFFFu, v_lit, o);
+            v_paths += __shfl_xor_sync(0xFFFFFFFFu, v_paths, o);
+        }
+        unsigned long long v_inner = tl.inner, v_leaf = tl.leaf, v_rect = tl.rect;
+        uint32_t v_ms = tl.max_stack;
+        if (CNT) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                v_inner += __shfl_xor_sync(0xFFFFFFFFu, v_inner, o);
+                v_leaf += __shfl_xor_sync(0xFFFFFFFFu, v_leaf, o);
+                v_rect += __shfl_xor_sync(0xFFFFFFFFu, v_rect, o);
+                v_ms = max(v_ms, __shfl_xor_sync(0xFFFFFFFFu, v_ms, o));
+            }
+        }
+        if ((tid & 31u) == 0u) {
+            atomicAdd(&P.counters->rays, v_rays);
+            atomicAdd(&P.counters->hits, v_hits);
+            atomicAdd(&P.counters->paths, v_paths);
+            if (v_lit) atomicAdd(&P.counters->literal_rays, v_lit);
+            if (CNT) {
+                atomicAdd(&P.counters->inner_visits, v_inner);
+                atomicAdd(&P.counters->leaf_visits, v_leaf);
+                atomicAdd(&P.counters->rect_tests, v_rect);
+                atomicMax(&P.counters->max_stack, (unsigned long long)v_ms);
+            }
+        }
+    }
+}
+
 template <bool CNT, bool DBG, int kBlockThreads>
 __global__ void __launch_bounds__(kBlockThreads, 1024 / kBlockThreads)
 trace_kernel(const __grid_constant__ KParams P) {
@@ -95,77 +171,145 @@ trace_kernel(const __grid_constant__ KParams P) {
         }
     }
 
-    // Per-pixel reduction in the reference's order (shaders.metal:343-366): pairs, quads, octets (the phases whose
-    // stride is < spp), then the pixel's first thread adds the octets serially and divides by spp.
-    const uint32_t tid = threadIdx.x;
-    float *rx = red, *ry = red + kBlockThreads, *rz = red + 2 * kBlockThreads;
-    rx[tid] = sample.x; ry[tid] = sample.y; rz[tid] = sample.z;
+    red[threadIdx.x] = sample.x; red[kBlockThreads + threadIdx.x] = sample.y; red[2 * kBlockThreads + threadIdx.x] = sample.z;
     __syncthreads();
+    block_epilogue<CNT, kBlockThreads>(P, red, active, flat, pxx, pxy, k, seg, nhits, nliteral, tl);
+}
+
+// ---- trace_kernel_rg: the same kernel with the block's paths RE-FORMED INTO WARPS at every segment boundary ---------------------
+// After the first diffuse bounce the rays of a warp have nothing in common, and the warp runs every segment for as long as
+// its slowest ray needs (17.4 of 32 lanes busy in the interior body).  How long a ray travels — and with it how many nodes it
+// visits — correlates with how steeply it points at the floor or the roof (|dir.y|: the maze is a 10-unit-high slab, rays near
+// the vertical end after a few nodes, near-horizontal ones cross many cells; trace replays in tools/sched_sim_r2.py).  So at
+// the end of every segment the block pushes the state of its live paths through shared memory, ordered by a 5-bit key on
+// |dir.y| (a counting sort: one shared-memory atomic per path, one warp scan), and each warp continues with 32 paths of similar
+// steepness; ended paths drop out, so the tail segments (paths kept alive by mirror hits) run in fewer, fuller warps.  Which lane
+// traces which path changes, nothing else: every path keeps its own RNG state, counters and home thread (the thread it started
+// on, where its sample is delivered for the pixel reduction), so every observable stays bit-identical.
+template <bool CNT, bool DBG, int kBlockThreads>
+__global__ void __launch_bounds__(kBlockThreads, 1024 / kBlockThreads)
+trace_kernel_rg(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *red = reinterpret_cast<float *>(smem_raw);                                  // 3 * kBlockThreads floats: samples by home thread
+    float4 *xch = reinterpret_cast<float4 *>(smem_raw + 3 * kBlockThreads * sizeof(float));   // 4 planes of kBlockThreads float4: path state in flight
+    uint32_t *hist = reinterpret_cast<uint32_t *>(xch + 4 * kBlockThreads);            // 2 x 32 bin counters (double-buffered)
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint64_t path = (uint64_t)blockIdx.x * kBlockThreads + tid;
+    const bool active = path < P.total_paths;
+    Tally tl = {0u, 0u, 0u, 0u};
+    uint32_t seg = 0, nhits = 0, nliteral = 0;                                         // per-lane event counts (summed over the grid at the end)
+    uint32_t pxx = 0, pxy = 0, k = 0, flat = 0;                                        // of the path this thread STARTED (its home pixel)
+    const uint32_t root = P.root_count ? (kLeafBit | P.root_link | (P.root_count << 24)) : P.root_link;
+    // the path this lane currently carries
+    V3 ori = mk(0.0f, 0.0f, 0.0f), dir = mk(1.0f, 1.0f, 1.0f), color = mk(1.0f, 1.0f, 1.0f), light = mk(0.0f, 0.0f, 0.0f);
+    uint32_t state = 0u, first_hit = 0xFFFFFFFFu, home = tid, pseg = 0;
+    int n = 0, mirror_hits = 0;
+    bool has = false;
+
+    if (active) {
+        const PathStart ps = start_path(P, path);
+        k = ps.k; flat = ps.flat; pxx = ps.pxx; pxy = ps.pxy;
+        ori = ps.ori; dir = ps.dir; state = ps.state;
+        has = 0 < P.bounce_limit;                                                      // :306, n = 0
+    }
+    red[tid] = 0.0f; red[kBlockThreads + tid] = 0.0f; red[2 * kBlockThreads + tid] = 0.0f;   // sqrt(max(0, 0)) of a path that never runs (:344)
+    if (DBG && active && !has) {
+        if (P.dbg_first_hit) P.dbg_first_hit[path] = 0xFFFFFFFFu;
+        if (P.dbg_segments) P.dbg_segments[path] = 0u;
+        if (P.dbg_mirror_hits) P.dbg_mirror_hits[path] = 0u;
+        if (P.dbg_radiance) { P.dbg_radiance[3 * path] = 0.0f; P.dbg_radiance[3 * path + 1] = 0.0f; P.dbg_radiance[3 * path + 2] = 0.0f; }
+    }
+    if (tid < 64) hist[tid] = 0u;          // kBlockThreads >= 64
+    uint32_t live = (uint32_t)__syncthreads_count(has);                                // paths of the block still running
+    uint32_t round = 0, n_rg = 0;
+    // P.rg_mask: bit r set = re-form the warps after segment r.  After the mask's last round the warps run on independently.
+    const uint32_t last_rg = P.rg_mask ? 32u - (uint32_t)__clz(P.rg_mask) : 0u;        // first round index without any later regroup
+
+    while (live > 0u) {
+        // ---- one segment for the lanes that carry a path (whole warps without one skip it) ----
+        if (__any_sync(0xFFFFFFFFu, has)) {
+            const bool lit = ray_is_literal(P, ori, dir);
+            const bool any_lit = __any_sync(0xFFFFFFFFu, has && lit) || !P.rect_fast_ok;
+            Hit h;
+            if (P.rcp_mode) {
+                if (!any_lit) h = traverse<false, CNT, true>(P.pairs, P.rects, root, has, false, ori, dir, 1e30f, 0xFFFFFFFFu, &tl);
+                else h = traverse<true, CNT, true>(P.pairs, P.rects, root, has, lit, ori, dir, 1e30f, 0xFFFFFFFFu, &tl);
+            } else {
+                if (!any_lit) h = traverse<false, CNT, false>(P.pairs, P.rects, root, has, false, ori, dir, 1e30f, 0xFFFFFFFFu, &tl);
+                else h = traverse<true, CNT, false>(P.pairs, P.rects, root, has, lit, ori, dir, 1e30f, 0xFFFFFFFFu, &tl);
+            }
+            if (has) {
+                if (lit) nliteral++;
+                seg++; pseg++;
+                bool alive = false;
+                if (h.t < 1e30f) {                                                     // :308, :336-339 (sky term is * 0.0)
+                    nhits++;
+                    uint32_t orig = 0xFFFFFFFFu;
+                    alive = shade_hit(P, h.slot, h.t, ori, dir, color, light, state, mirror_hits, (DBG && n == 0) ? &orig : nullptr);
+                    if (DBG && n == 0) first_hit = orig;
+                    n++;
+                    alive = alive && (n < P.bounce_limit + mirror_hits);               // :306
+                }
+                if (!alive) {                                                          // the path is over: its sample goes home (:344)
+                    red[home] = fsqrt(fmaxf(light.x, 0.0f)); red[kBlockThreads + home] = fsqrt(fmaxf(light.y, 0.0f));
+                    red[2 * kBlockThreads + home] = fsqrt(fmaxf(light.z, 0.0f));
+                    if (DBG) {
+                        const uint64_t hp = (uint64_t)blockIdx.x * kBlockThreads + home;
+                        if (P.dbg_first_hit) P.dbg_first_hit[hp] = first_hit;
+                        if (P.dbg_segments) P.dbg_segments[hp] = pseg;
+                        if (P.dbg_mirror_hits) P.dbg_mirror_hits[hp] = (uint32_t)mirror_hits;
+                        if (P.dbg_radiance) { P.dbg_radiance[3 * hp] = light.x; P.dbg_radiance[3 * hp + 1] = light.y; P.dbg_radiance[3 * hp + 2] = light.z; }
+                    }
+                    has = false;
+                }
+            }
+        }
+        if (round >= 32u || !((P.rg_mask >> round) & 1u)) {                            // no regroup after this segment
+            round++;
+            if (round >= last_rg && !__any_sync(0xFFFFFFFFu, has)) break;              // nothing left to wait for: this warp is done
+            continue;
+        }
+        // ---- re-form the warps: counting sort of the live paths by |dir.y| (dir is normalised: :321, :329) ----
+        uint32_t *h_now = hist + 32u * (n_rg & 1u), *h_next = hist + 32u * ((n_rg + 1u) & 1u);
+        n_rg++;
+        const uint32_t bin = min(31u, (uint32_t)(fabsf(dir.y) * 32.0f));
+        uint32_t pos = 0;
+        if (has) pos = atomicAdd(h_now + bin, 1u);
+        if (tid < 32) h_next[tid] = 0u;
+        __syncthreads();
+        const uint32_t c = h_now[lane];
+        uint32_t incl = c;
 #pragma unroll
-    for (uint32_t stride = 1; stride <= 4; stride *= 2) {
-        if (stride < P.spp && (tid & (2 * stride - 1)) == 0) {
-            rx[tid] = fadd(rx[tid], rx[tid + stride]);
-            ry[tid] = fadd(ry[tid], ry[tid + stride]);
-            rz[tid] = fadd(rz[tid], rz[tid + stride]);
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += v;
+        }
+        live = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const uint32_t start = __shfl_sync(0xFFFFFFFFu, incl - c, bin);
+        if (has) {
+            const uint32_t r = start + pos;
+            xch[r] = make_float4(ori.x, ori.y, ori.z, dir.x);
+            xch[kBlockThreads + r] = make_float4(dir.y, dir.z, color.x, color.y);
+            xch[2 * kBlockThreads + r] = make_float4(color.z, light.x, light.y, light.z);
+            xch[3 * kBlockThreads + r] = make_float4(__uint_as_float(state), __uint_as_float((uint32_t)n | ((uint32_t)mirror_hits << 16)),
+                                                     __uint_as_float(home | (pseg << 12)), __uint_as_float(first_hit));
         }
         __syncthreads();
+        has = tid < live;
+        if (has) {
+            const float4 a = xch[tid], b = xch[kBlockThreads + tid], cc = xch[2 * kBlockThreads + tid], d = xch[3 * kBlockThreads + tid];
+            ori = mk(a.x, a.y, a.z); dir = mk(a.w, b.x, b.y); color = mk(b.z, b.w, cc.x); light = mk(cc.y, cc.z, cc.w);
+            state = __float_as_uint(d.x);
+            const uint32_t nm = __float_as_uint(d.y), hs = __float_as_uint(d.z);
+            n = (int)(nm & 0xFFFFu); mirror_hits = (int)(nm >> 16);
+            home = hs & 0xFFFu; pseg = hs >> 12;
+            first_hit = __float_as_uint(d.w);
+        }
+        round++;
     }
-    if (active && (flat & (P.spp - 1)) == 0) {
-        float sx = rx[tid], sy = ry[tid], sz = rz[tid];
-        for (uint32_t i = 1; i < P.spp / 8; i++) {
-            sx = fadd(sx, rx[tid + 8 * i]); sy = fadd(sy, ry[tid + 8 * i]); sz = fadd(sz, rz[tid + 8 * i]);
-        }
-        const float d = (float)(int)P.spp;
-        float4 px = make_float4(fdiv(sx, d), fdiv(sy, d), fdiv(sz, d), 1.0f);
-        if (P.quant8) px = quant8(px);
-        if (P.image && pxx < P.W && pxy < P.H) reinterpret_cast<float4 *>(P.image)[(size_t)pxy * P.W + pxx] = px;
-        if (P.tiles) reinterpret_cast<float4 *>(P.tiles)[(size_t)k * P.ppc + (flat >> P.log2_spp)] = px;
-        if ((P.n_peers || P.host_out) && pxx < P.W && pxy < P.H) {
-            const size_t at = (size_t)pxy * P.W + pxx;
-            if (P.host_out) reinterpret_cast<float4 *>(P.host_out)[at] = px;        // zero-copy output: mapped pinned host frame, over PCIe
-            if (P.peers_multicast) {                                    // fused exchange, NVSwitch multicast: one store, replicated by the switch
-                float4 *mc = reinterpret_cast<float4 *>(P.peers[0]) + at;
-                asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(px.x), "f"(px.y), "f"(px.z), "f"(px.w) : "memory");
-            } else {                                                    // fused exchange, NVLink peer mappings: one store per rank's frame
-                for (uint32_t i = 0; i < P.n_peers; i++) reinterpret_cast<float4 *>(P.peers[i])[at] = px;
-            }
-        }
-    }
-
-    // Event counts: warp-reduce, one atomic per warp and counter.
-    {
-        unsigned long long v_rays = seg, v_hits = nhits, v_lit = nliteral, v_paths = active ? 1u : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            v_rays += __shfl_xor_sync(0xFFFFFFFFu, v_rays, o);
-            v_hits += __shfl_xor_sync(0xFFFFFFFFu, v_hits, o);
-            v_lit += __shfl_xor_sync(0xFFFFFFFFu, v_lit, o);
-            v_paths += __shfl_xor_sync(0xFFFFFFFFu, v_paths, o);
-        }
-        unsigned long long v_inner = tl.inner, v_leaf = tl.leaf, v_rect = tl.rect;
-        uint32_t v_ms = tl.max_stack;
-        if (CNT) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                v_inner += __shfl_xor_sync(0xFFFFFFFFu, v_inner, o);
-                v_leaf += __shfl_xor_sync(0xFFFFFFFFu, v_leaf, o);
-                v_rect += __shfl_xor_sync(0xFFFFFFFFu, v_rect, o);
-                v_ms = max(v_ms, __shfl_xor_sync(0xFFFFFFFFu, v_ms, o));
-            }
-        }
-        if ((tid & 31u) == 0u) {
-            atomicAdd(&P.counters->rays, v_rays);
-            atomicAdd(&P.counters->hits, v_hits);
-            atomicAdd(&P.counters->paths, v_paths);
-            if (v_lit) atomicAdd(&P.counters->literal_rays, v_lit);
-            if (CNT) {
-                atomicAdd(&P.counters->inner_visits, v_inner);
-                atomicAdd(&P.counters->leaf_visits, v_leaf);
-                atomicAdd(&P.counters->rect_tests, v_rect);
-                atomicMax(&P.counters->max_stack, (unsigned long long)v_ms);
-            }
-        }
-    }
+    __syncthreads();
+    block_epilogue<CNT, kBlockThreads>(P, red, active, flat, pxx, pxy, k, seg, nhits, nliteral, tl);
 }
 
 // De-interleave gathered tiles into the frame (consumer side of the multi-GPU tile gather).
@@ -289,6 +433,13 @@ __global__ void __launch_bounds__(256) mb_ffma_kernel(uint32_t iters, float *__r
 }
 
 template <bool C, bool D>
+const void *kptr_rg(int bt) {
+    if (bt == 64) return reinterpret_cast<const void *>(&trace_kernel_rg<C, D, 64>);
+    if (bt == 128) return reinterpret_cast<const void *>(&trace_kernel_rg<C, D, 128>);
+    return reinterpret_cast<const void *>(&trace_kernel_rg<C, D, kLargeBlock>);
+}
+
+template <bool C, bool D>
 const void *kptr(int bt) {
     return bt == kSmallBlock ? reinterpret_cast<const void *>(&trace_kernel<C, D, kSmallBlock>)
                              : reinterpret_cast<const void *>(&trace_kernel<C, D, kLargeBlock>);
@@ -297,6 +448,10 @@ const void *kptr(int bt) {
 }  // namespace
 
 const void *kernel_ptr(KernelChoice c) {
+    if (c.regroup) {
+        if (c.debug) return kptr_rg<true, true>(c.block_threads);
+        return c.counters ? kptr_rg<true, false>(c.block_threads) : kptr_rg<false, false>(c.block_threads);
+    }
     if (c.debug) return kptr<true, true>(c.block_threads);
     return c.counters ? kptr<true, false>(c.block_threads) : kptr<false, false>(c.block_threads);
 }

@@ -68,6 +68,7 @@ struct KParams {
     uint32_t force_literal;
     uint32_t rcp_mode;         // MM_FLAG_RCP_SLAB: slab quotients as (b - o) * RN(1/d)
     uint32_t scene_fast_ok;
+    uint32_t rg_mask;          // trace_kernel_rg: bit r set = re-form the block's warps after segment r
     uint32_t quant8;           // MM_FLAG_SCREEN_RGBA8: stored pixels are quantised to k/255 (round to nearest even)
     uint64_t total_paths;
     const PairRec *pairs;
@@ -103,7 +104,7 @@ constexpr int kLargeBlock = 256;
 inline int block_threads_for(uint32_t spp) { return spp <= (uint32_t)kSmallBlock ? kSmallBlock : kLargeBlock; }
 
 // Returns the kernel's static properties for the occupancy query and launch.
-struct KernelChoice { bool counters, debug; int block_threads; bool pool; };
+struct KernelChoice { bool counters, debug; int block_threads; bool pool; bool regroup; };
 const void *kernel_ptr(KernelChoice c);
 const void *pool_kernel_ptr(KernelChoice c);
 cudaError_t launch_pool(const KParams &p, KernelChoice c, unsigned blocks, unsigned threads, size_t smem_bytes, cudaStream_t stream);
