@@ -269,7 +269,7 @@ class SharedHostFrame:
     """One frame buffer in host memory shared by every rank of the node (a file in /dev/shm mapped by all), pinned and mapped
     into each rank's CUDA context with mm_host_register: every rank's kernel stores its pixels straight into it."""
 
-    def __init__(self, mm, name, nbytes, create):
+    def __init__(self, mm, name, nbytes, create, register=True):
         import mmap
         import numpy as np
         self.path = os.path.join("/dev/shm", name)
@@ -279,15 +279,17 @@ class SharedHostFrame:
         self.f = open(self.path, "r+b")
         self.map = mmap.mmap(self.f.fileno(), nbytes)
         self.array = np.frombuffer(self.map, dtype=np.float32)
-        self.lib = mm.load_library()
         self.ptr = self.array.ctypes.data
-        rc = self.lib.mm_host_register(self.ptr, nbytes)
-        if rc != 0:
-            raise RuntimeError(f"mm_host_register on the shared frame failed: {rc}")
+        self.lib = mm.load_library() if register else None           # register=False: CPU tests of the plumbing
+        if register:
+            rc = self.lib.mm_host_register(self.ptr, nbytes)
+            if rc != 0:
+                raise RuntimeError(f"mm_host_register on the shared frame failed: {rc}")
         self.create = create
 
     def close(self):
-        self.lib.mm_host_unregister(self.ptr)
+        if self.lib is not None:
+            self.lib.mm_host_unregister(self.ptr)
         self.array = None
         try:
             self.map.close()

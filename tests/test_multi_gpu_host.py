@@ -89,3 +89,63 @@ def test_gloo_world2_gather_and_scatter(mm, oracle):
     for pr in procs:
         pr.join(timeout=60)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def _shared_frame_worker(rank, world, port, q):
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import torch.distributed as dist
+
+    import bench
+    import mirror_maze_b200 as mm
+    from oracle import oracle
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        noise = mm.load_noise()
+        sc, u, p, ch = build_case(mm, "ragged")                       # 84 groups, frame not a multiple of the chunk
+        H, W = int(u.view_height), int(u.view_width)
+        name = f"mm_test_frame_{port}"
+        shared = bench.SharedHostFrame(mm, name, H * W * 16, create=True, register=False) if rank == 0 else None
+        dist.barrier()
+        if rank != 0:
+            shared = bench.SharedHostFrame(mm, name, H * W * 16, create=False, register=False)
+        mine = mm.Params.from_buffer_copy(bytes(p))
+        mine.group_first, mine.group_step, mine.group_count = mm.tile_partition(p.grid_x * p.grid_y, rank, world)
+        # every rank writes only the pixels of its own groups into the ONE frame (what the kernels' zero-copy stores do)
+        oracle.render(sc, noise, u, mine, ch, out=shared.array.reshape(H, W, 4))
+        dist.barrier()
+        ok = True
+        if rank == 0:
+            full = oracle.render(sc, noise, u, p, ch)[0]
+            ok = shared.array.tobytes() == full.tobytes()
+        dist.barrier()
+        shared.close()
+        q.put((rank, ok))
+    except Exception as e:
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_shared_host_frame_assembly(mm, oracle):
+    """bench.py's N > 1 end-to-end leg: every rank stores the pixels of its interleaved groups into one frame in shared host
+    memory (/dev/shm mapping; on a GPU box it is also pinned + mapped into each rank's CUDA context) — the union is the
+    one-rank frame, no gather and no copy."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shared_frame_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)]
