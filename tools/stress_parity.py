@@ -23,7 +23,8 @@ def main():
             if i % 7 == 0:
                 center = (-half + 10.0 * cell[0], center[1], center[2])            # exactly on a wall-plane coordinate
             u = mm.default_uniform(maze, 96, 64, 4, time=int(rng.integers(0, 100000)), camera_center=center, half_theta=float(rng.uniform(0.0, np.pi)))
-            p = mm.full_frame_params(u, spp=int(rng.choice([1, 4, 8, 16])), bounce_limit=int(rng.integers(1, 12)), mirror_limit=int(rng.choice([2, 15])), flags=mm.FLAG_COUNTERS)
+            kernel = (0, mm.FLAG_POOL_KERNEL, mm.FLAG_REGROUP)[i % 3]               # the shipped kernel and the two opt-in scheduling kernels
+            p = mm.full_frame_params(u, spp=int(rng.choice([1, 4, 8, 16])), bounce_limit=int(rng.integers(1, 12)), mirror_limit=int(rng.choice([2, 15])), flags=mm.FLAG_COUNTERS | kernel)
             img, cnt, dbg = r.render(u, p, ch, debug=True)
             rimg, rcnt, rdbg = oracle.render(sc, noise, u, p, ch, debug=True)
             ok = img.tobytes() == rimg.tobytes() and all(dbg[k].tobytes() == rdbg[k].tobytes() for k in dbg) and \
@@ -32,7 +33,7 @@ def main():
             rays += cnt["rays"]; lit += cnt["literal_rays"]
             if not ok:
                 print("MISMATCH maze", maze, "pose", i, center)
-    print(f"stress parity: {n_poses} poses over mazes 10/32/64/128, {rays} rays ({lit} on the literal-divide path), mismatches: {bad}, {time.time() - t0:.1f} s")
+    print(f"stress parity: {n_poses} poses over mazes 10/32/64/128 (kernels: shipped / pool / regroup in turn), {rays} rays ({lit} on the literal-divide path), mismatches: {bad}, {time.time() - t0:.1f} s")
     r.close()
     bad += against_reference_shader(noise, max(8, n_poses // 5))
     return 1 if bad else 0
