@@ -680,6 +680,7 @@ def run_flythroughs(a, mm, torch, dist, rank, world, local):
         gx -= 1
     p = mm.Params(spp=a.spp, bounce_limit=a.bounces, mirror_limit=a.mirror_limit, grid_x=gx, grid_y=per_frame // gx)
     hf = mm.HostFrame(a.height, a.width)
+    hf2 = mm.HostFrame(a.height, a.width)
 
     def fly(seed, frames, check=None):
         bag = mm.ChunkBag(a.width, a.height, 4, seed=1000 + seed)
@@ -702,9 +703,14 @@ def run_flythroughs(a, mm, torch, dist, rank, world, local):
             uu.time = f
             ch = bag.next(per_frame)
             rays += r.render_into(uu, p, ch.ctypes.data, len(ch), None)["rays"]   # compute pass into the persistent screen
-            r.present(hf.array)                                                 # present pass (blur) + read-back of the frame
             if check is not None:
+                r.present(hf.array)                                             # present pass (blur) + read-back, synchronous
                 check(f, uu, ch)
+            else:
+                # present pass without the wait (main.rs:888-894): the frame's read-back overlaps the next frame's dispatch;
+                # two pinned host frames alternate
+                r.present_async((hf if f & 1 else hf2).ptr)
+        r.wait_present()
         return rays
 
     # parity: the first 3 frames of this rank's fly-through against the oracle + the blur model, on a fresh renderer state
@@ -756,7 +762,8 @@ def run_flythroughs(a, mm, torch, dist, rank, world, local):
                           "n_gpus": world, "steps": int(a.frames), "warmup": 0, "ms_per_step": round(1e3 * tot[2] / a.frames, 4), "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": f"{world} fly-through(s) x {a.frames} frames, {a.maze}x{a.maze} maze, {a.width}x{a.height}, {a.spp} spp, {a.bounces} bounces, "
-                                                 f"1/64 of the screen ({per_frame} chunks) re-rendered per frame + 5-tap present blur, frame read back to pinned host memory every frame",
+                                                 f"1/64 of the screen ({per_frame} chunks) re-rendered per frame + 5-tap present blur, every frame read back to pinned host memory "
+                                                 f"(mm_present_async: the read-back overlaps the next frame's dispatch)",
                                      "workload_id": "cfg5", "parallelism": "one fly-through per GPU, no exchange until the final collect"},
                           "Mrays_per_s": round(tot[0] / tot[2] / 1e6, 1), "parity_ok": bool(tot[3] == 1.0) if parity_ok is not None else None,
                           "parity": "first 3 frames of every rank's fly-through == oracle render + blur model, bit for bit",

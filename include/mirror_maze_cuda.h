@@ -271,6 +271,13 @@ int mm_present(mm_ctx *ctx, float *out_rgba);
  * quantised, like fragment_shader's store into the 8-bit drawable / screen texture.  out_rgba (H*W*4 floats, values k/255) and
  * out_rgba8 (H*W*4 bytes, the texels themselves) may each be null.  Synchronous. */
 int mm_present_rgba8(mm_ctx *ctx, float *out_rgba, uint8_t *out_rgba8);
+/* The present pass without the wait, as the reference's loop runs it (present_drawable + commit and on to the next frame,
+ * main.rs:888-894): blur on the context's stream, then the blurred screen is snapshot on the device and read back into
+ * out_rgba on a second stream, so the next dispatch overlaps the 16 bytes per pixel going over PCIe.  out_rgba must be pinned
+ * host memory (mm_host_alloc / mm_host_register) and stay untouched until mm_wait_present returns; a later mm_present_async
+ * into another buffer queues behind it. */
+int mm_present_async(mm_ctx *ctx, float *out_rgba);
+int mm_wait_present(mm_ctx *ctx);
 int mm_present_blur_device(mm_ctx *ctx, const float *d_src, float *d_dst, uint32_t width, uint32_t height);
 
 /*

@@ -141,6 +141,8 @@ PROTOTYPES = {
     "mm_microbench": (C.c_int, [_vp, C.c_int, C.c_uint64, _P(C.c_double)]),
     "mm_present": (C.c_int, [_vp, _vp]),
     "mm_present_rgba8": (C.c_int, [_vp, _vp, _vp]),
+    "mm_present_async": (C.c_int, [_vp, _vp]),
+    "mm_wait_present": (C.c_int, [_vp]),
     "mm_present_blur_device": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32]),
     "mm_move_camera": (C.c_int, [_vp, C.c_uint32, Float3, Float4, _vp, C.c_uint32, C.c_float, _P(Float3)]),
     "mm_bag_new": (C.c_int, [C.c_float, C.c_float, C.c_uint32, C.c_uint64, _P(_vp)]),

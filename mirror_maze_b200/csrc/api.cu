@@ -104,6 +104,10 @@ int mm_destroy(mm_ctx *ctx) {
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaFree(ctx->d_screen8);
+    cudaFree(ctx->d_snap);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_snap) cudaEventDestroy(ctx->ev_snap);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return MM_OK;
@@ -340,7 +344,9 @@ int ensure_screen(mm_ctx *ctx, uint32_t W, uint32_t H) {
     cudaFree(ctx->d_screen);
     cudaFree(ctx->d_screen2);
     cudaFree(ctx->d_screen8);
-    ctx->d_screen = nullptr; ctx->d_screen2 = nullptr; ctx->d_screen8 = nullptr;
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    cudaFree(ctx->d_snap);
+    ctx->d_screen = nullptr; ctx->d_screen2 = nullptr; ctx->d_screen8 = nullptr; ctx->d_snap = nullptr;
     CK(cudaMalloc(&ctx->d_screen, (size_t)W * H * 4 * sizeof(float)));
     CK(cudaMemsetAsync(ctx->d_screen, 0, (size_t)W * H * 4 * sizeof(float), ctx->stream));
     ctx->screen_w = W; ctx->screen_h = H;
@@ -469,6 +475,7 @@ int mm_render_async(mm_ctx *ctx, const mm_uniform *uni, const mm_params *params,
     if (!ctx) return MM_ERR_INVALID;
     ctx->err.clear();
     int rc;
+    CK(cudaSetDevice(ctx->device));
     if (ctx->in_flight && (rc = mm_wait(ctx, nullptr)) != MM_OK) return rc;     // one host-buffer frame in flight per context
     if (chunks) {
         if ((rc = mm_set_chunks(ctx, chunks, n_chunks)) != MM_OK) return rc;
@@ -612,6 +619,44 @@ static int present_impl(mm_ctx *ctx, float *out_rgba, bool q8, uint8_t *out_rgba
     return MM_OK;
 }
 int mm_present(mm_ctx *ctx, float *out_rgba) { return present_impl(ctx, out_rgba, false, nullptr); }
+
+int mm_wait_present(mm_ctx *ctx) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!ctx->present_in_flight) return MM_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev_copy));
+    ctx->present_in_flight = false;
+    return MM_OK;
+}
+
+int mm_present_async(mm_ctx *ctx, float *out_rgba) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!ctx->d_screen) return fail(ctx, MM_ERR_INVALID, "mm_present_async: nothing rendered yet");
+    const size_t bytes = (size_t)ctx->screen_w * ctx->screen_h * 4 * sizeof(float);
+    if (!out_rgba || !host_device_alias(out_rgba, bytes))
+        return fail(ctx, MM_ERR_INVALID, "mm_present_async: out_rgba must be pinned host memory (mm_host_alloc / mm_host_register); use mm_present otherwise");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_snap, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+    }
+    if (!ctx->d_screen2) CK(cudaMalloc(&ctx->d_screen2, bytes));
+    if (!ctx->d_snap) CK(cudaMalloc(&ctx->d_snap, bytes));
+    CK(launch_blur(ctx->d_screen, ctx->d_screen2, ctx->screen_w, ctx->screen_h, ctx->stream));
+    float *t = ctx->d_screen; ctx->d_screen = ctx->d_screen2; ctx->d_screen2 = t;   // the blurred image is the screen now
+    // snapshot for the read-back: the next dispatch may write into the screen while the copy is still on the wire
+    if (ctx->present_in_flight) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));       // the previous snapshot has left the device
+    CK(cudaMemcpyAsync(ctx->d_snap, ctx->d_screen, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_snap, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_snap, 0));
+    CK(cudaMemcpyAsync(out_rgba, ctx->d_snap, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    ctx->present_in_flight = true;
+    return MM_OK;
+}
 int mm_present_rgba8(mm_ctx *ctx, float *out_rgba, uint8_t *out_rgba8) { return present_impl(ctx, out_rgba, true, out_rgba8); }
 
 int mm_microbench(mm_ctx *ctx, int kind, uint64_t table_bytes, double *result) {

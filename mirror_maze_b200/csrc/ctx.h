@@ -40,6 +40,11 @@ struct mm_ctx {
     size_t pending_bytes = 0;
     bool in_flight = false;
     uint32_t last_zero_copy = 0;
+    // asynchronous present (mm_present_async): the blurred screen is snapshot on the main stream and read back on a second one
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_copy = nullptr;
+    float *d_snap = nullptr;
+    bool present_in_flight = false;
     // last launch facts
     uint32_t last_smem = 0, last_blocks_per_sm = 0, last_block_threads = 0;
     const void *cfg_fn = nullptr;     // kernel variant whose attributes / occupancy were last set up

@@ -198,6 +198,13 @@ class Renderer:
         self._ck(self._lib.mm_present(self._ctx, out.ctypes.data if copy else None))
         return out
 
+    def present_async(self, out_ptr):
+        """mm_present_async: blur + read-back into pinned host memory on a second stream; returns at once."""
+        self._ck(self._lib.mm_present_async(self._ctx, out_ptr))
+
+    def wait_present(self):
+        self._ck(self._lib.mm_wait_present(self._ctx))
+
     def present_rgba8(self, out=None, out_bytes=None):
         """mm_present_rgba8: the present blur on an RGBA8Unorm screen; fills the float frame (values k/255) and / or the
         uint8 [H, W, 4] texel array."""

@@ -157,3 +157,37 @@ def test_rgba8_screen_mode_matches_oracle_and_blur_model(mm, oracle, noise, scen
         assert out.tobytes() == screen.tobytes()
         assert np.array_equal(out8, np.rint(screen * np.float32(255.0)).astype(np.uint8))
     r.close()
+
+
+@pytest.mark.gpu
+def test_present_async_delivers_the_frames_of_the_synchronous_present(mm, noise, scenes):
+    """mm_present_async (blur, device snapshot, read-back on a second stream while the next dispatch runs) into two alternating
+    pinned frames == mm_present frame by frame; an unpinned buffer is refused."""
+    from cases import build_case
+
+    sc, u, p, ch = build_case(mm, "yaw", scenes)
+    H, W = int(u.view_height), int(u.view_width)
+    ra, rb = mm.Renderer(0), mm.Renderer(0)
+    ra.upload_scene(sc, noise); rb.upload_scene(sc, noise)
+    frames = [mm.HostFrame(H, W), mm.HostFrame(H, W)]
+    half = mm.Params.from_buffer_copy(bytes(p))
+    n = p.grid_x * p.grid_y
+    expect = []
+    for f in range(6):
+        half.group_first, half.group_step, half.group_count = f % 3, 3, (n - f % 3 + 2) // 3
+        u.time = f
+        ra.render(u, half, ch)
+        out = np.empty((H, W, 4), np.float32)
+        ra.present(out)
+        expect.append(out)
+        rb.render(u, half, ch)                             # frame f's dispatch overlaps frame f - 1's read-back (even f - 1)
+        rb.present_async(frames[f & 1].ptr)
+        if f & 1:                                          # every second frame: wait, then both buffers hold finished frames
+            rb.wait_present()
+            assert frames[1].array.tobytes() == expect[f].tobytes(), f
+            assert frames[0].array.tobytes() == expect[f - 1].tobytes(), f
+    with pytest.raises(mm.MMError):
+        rb.present_async(np.empty((H, W, 4), np.float32).ctypes.data)
+    ra.close(); rb.close()
+    for fr in frames:
+        fr.close()
