@@ -4,10 +4,13 @@ instructions per interior visit, 80 per rect test, 8 per vote, 330 per shaded se
 (segment-synchronous warps, interior body while nI >= 6 nL, four visits per vote) reproduces the measured 17.4 lanes per
 interior-body instruction, which is what makes the other rows worth reading.
 
-    python tools/sched_sim_r2.py regroup | pool | threeway      (maze 32, every 797th chunk group of the 1080p frame)
+    python tools/sched_sim_r2.py regroup | pool | threeway | soft | pair      (maze 32, every 797th chunk group of the 1080p frame)
 
 regroup   upper bound of re-forming warps inside a block at every segment boundary: rays sorted by their TRUE visit count
 threeway  one warp, lanes desynchronised across segments: a vote picks interior / leaf / shade+set-up
+soft      soft segment boundaries: shade and restart the finished lanes as soon as at most k stragglers are still traversing
+pair      cooperative interior body: a finished lane takes one of the two slab tests of a still-traversing lane (42 instead of 59
+          instructions per visit) whenever every traversing lane can get such a helper
 pool      persistent warp over a pool of M paths in shared memory with per-body ready queues (built: pool_kernel.cu)
 """
 import os, pickle, random, sys
@@ -185,6 +188,77 @@ def run_pool(paths, gI=55.0, gL=30.0, gS=40.0, cS=300.0, cV=12.0, gen=60.0):
         print(f"pool M={M:3d}, {N} visits per batch, threshold {th}: {tot / rays:6.1f} warp-instr/ray, {lanes[0] / lanes[1]:.1f} lanes per interior exec")
 
 
+def run_soft(paths):
+    warps = [paths[i:i + 32] for i in range(0, len(paths), 32)][:800]
+    rays = sum(len(p) for w in warps for p in w)
+    for k in (0, 1, 2, 4, 8):
+        tot, li, ni, ns, ls = 0.0, 0, 0, 0, 0
+        for w in warps:
+            ev = [path_events(p) for p in w]; pos = [0] * len(ev)
+            while True:
+                I = [i for i in range(len(ev)) if pos[i] < len(ev[i]) and ev[i][pos[i]] == 0]
+                L = [i for i in range(len(ev)) if pos[i] < len(ev[i]) and ev[i][pos[i]] > 0]
+                S = [i for i in range(len(ev)) if pos[i] < len(ev[i]) and ev[i][pos[i]] == -1]
+                if not (I or L or S):
+                    break
+                if S and len(I) + len(L) <= k:                       # k = 0 is the shipped kernel
+                    tot += C_S + 40; ns += 1; ls += len(S)
+                    for i in S:
+                        pos[i] += 1
+                    continue
+                tot += C_V
+                if I and len(I) >= 6 * len(L):
+                    for _ in range(4):
+                        act = [i for i in I if pos[i] < len(ev[i]) and ev[i][pos[i]] == 0]
+                        if not act:
+                            break
+                        tot += C_I; li += len(act); ni += 1
+                        for i in act:
+                            pos[i] += 1
+                else:
+                    tot += C_L * max(ev[i][pos[i]] for i in L)
+                    for i in L:
+                        pos[i] += 1
+        print(f"soft boundary, {k} stragglers allowed: {tot / rays:6.1f} warp-instr/ray, {li / ni:.1f} lanes per interior exec, "
+              f"{ns / len(warps):.1f} shade execs per warp at {ls / ns:.1f} lanes")
+
+
+def run_pair(paths, c_pair=42.0, c_setup=30.0):
+    warps = [paths[i:i + 32] for i in range(0, len(paths), 32)][:800]
+    rays = sum(len(p) for w in warps for p in w)
+    for pair in (False, True):
+        tot, execs, paired = 0.0, 0, 0
+        for w in warps:
+            for s in range(max(len(p) for p in w)):
+                ev = [seg_events(p[s]) for p in w if len(p) > s]
+                n = len(ev); pos = [0] * n; helped = set(); free = 32 - n
+                while True:
+                    I = [i for i in range(n) if pos[i] < len(ev[i]) and ev[i][pos[i]] == 0]
+                    L = [i for i in range(n) if pos[i] < len(ev[i]) and ev[i][pos[i]] != 0]
+                    if not I and not L:
+                        break
+                    tot += C_V
+                    if I and len(I) >= 6 * len(L):
+                        active = [i for i in range(n) if pos[i] < len(ev[i])]
+                        avail = free + (n - len(active)) - sum(1 for o in active if o in helped)
+                        need = [o for o in I if o not in helped]
+                        use = pair and len(need) <= avail
+                        if use and need:
+                            tot += c_setup; helped.update(need)
+                        for _ in range(4):
+                            act = [i for i in I if pos[i] < len(ev[i]) and ev[i][pos[i]] == 0]
+                            if not act:
+                                break
+                            tot += c_pair if use else C_I; execs += 1; paired += 1 if use else 0
+                            for i in act:
+                                pos[i] += 1
+                    else:
+                        tot += C_L * max(ev[i][pos[i]] for i in L)
+                        for i in L:
+                            pos[i] += 1
+        print(f"{'pair mode' if pair else 'shipped  '}: {tot / rays:6.1f} traversal warp-instr/ray, {paired / max(execs, 1):.3f} of the interior execs in pair mode")
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "threeway"
-    {"regroup": run_regroup, "threeway": run_threeway, "pool": run_pool}[mode](traces())
+    {"regroup": run_regroup, "threeway": run_threeway, "pool": run_pool, "soft": run_soft, "pair": run_pair}[mode](traces())
