@@ -379,21 +379,30 @@ def test_unguarded_edge_lengths_take_the_literal_rect_test(mm, oracle, noise, sc
     r.close()
 
 
-def test_full_size_frame_equals_oracle(mm, noise, scenes, renderer):
-    """BASELINE configs[1] at FULL size — 32x32 maze, 1920x1080, 16 spp, 8 bounces, 33.2 M paths, 268 M rays — the whole
-    frame and every counter against the CPU oracle (about 10-20 s of host time on the GPU box's cores)."""
+@pytest.mark.parametrize("maze", [32, 64, 256])
+def test_full_size_frame_equals_oracle(mm, noise, scenes, maze):
+    """BASELINE configs[1] (32x32 maze), the north-star headline (64x64) and configs[3] (256x256) at FULL size — 1920x1080, 16 spp,
+    8 bounces, 33.2 M paths, about 265 M rays each — the whole frame and every counter against the CPU oracle (10-20 s of host
+    time per maze on the GPU box's cores)."""
     from oracle import oracle as o
 
-    sc = scenes(32)
-    renderer.upload_scene(sc, noise)
-    u = mm.default_uniform(32, 1920, 1080, 4)
+    sc = scenes(maze)
+    r = mm.Renderer(0)
+    r.upload_scene(sc, noise)
+    u = mm.default_uniform(maze, 1920, 1080, 4)
     ch = mm.gen_chunks(1920, 1080, 4)
     p = mm.full_frame_params(u, spp=16, bounce_limit=8, flags=mm.FLAG_COUNTERS)
-    img, cnt, _ = renderer.render(u, p, ch)
+    img, cnt, _ = r.render(u, p, ch)
     ref, rcnt, _ = o.render(sc, noise, u, p, ch)
     assert img.tobytes() == ref.tobytes()
     for k in COUNTER_KEYS:
         assert cnt[k] == rcnt[k], k
+    p.flags = 0                                              # the timed (non-counting) kernel variant, zero-copy into pinned memory
+    hf = mm.HostFrame(1080, 1920)
+    chunks = np.ascontiguousarray(ch)
+    c2 = r.render_into(u, p, chunks.ctypes.data, len(chunks), hf.ptr)
+    assert hf.array.tobytes() == ref.tobytes() and c2["rays"] == rcnt["rays"]
+    hf.close(); r.close()
 
 
 def test_scatter_gathered_single_launch(mm, noise, scenes, renderer):
