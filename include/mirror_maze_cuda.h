@@ -80,6 +80,16 @@ typedef struct mm_params {
 
 #define MM_FLAG_COUNTERS      1u   /* fill mm_counters beyond `rays` (slower kernel variant)          */
 #define MM_FLAG_FORCE_LITERAL 2u   /* use the literal-divide traversal for every ray (validation)     */
+#define MM_FLAG_RCP_SLAB     64u   /* opt-in arithmetic variant: slab quotients (b - o) * RN(1/d) instead of the literal
+                                      (b - o) / d of shaders.metal:88-93 — what a fast-math compile of the shader amounts to.
+                                      NOT the default; the oracle implements the same rule under the same flag and the
+                                      kernel matches it bit for bit, but results differ from the literal mode's.       */
+#define MM_FLAG_NO_ZERO_COPY 128u  /* mm_render / mm_render_async: copy the screen with a DMA transfer even when out_rgba is mapped pinned
+                                      memory the kernel could store into directly (for comparisons)                        */
+#define MM_FLAG_POOL_KERNEL  256u   /* trace with the persistent ray-pool kernel (pool_kernel.cu: warps own a pool of paths in shared
+                                      memory and run interior / leaf / shade bodies on work queues) instead of the default
+                                      one-thread-per-path kernel (render_kernel.cu).  Same bits; measured slower on B200
+                                      (profiles/r2_pool_kernel.md), kept as the evidence for that design                    */
 #define MM_FLAG_SCREEN_RGBA8 512u   /* the screen is an RGBA8Unorm texture, as the reference's is (main.rs:702-709): every pixel the dispatch
                                       stores is quantised per channel to rte(clamp(v, 0, 1) * 255) / 255 — what a read of the RGBA8Unorm
                                       texel returns (Metal's float -> unorm8 conversion rounds to nearest even) — so the persistent
@@ -89,16 +99,6 @@ typedef struct mm_params {
                                       the block's live paths are re-formed into warps through shared memory, sorted by ray steepness
                                       |dir.y|, ended paths dropped.  Same bits; fewer instructions (-14 % interior-body executions) but
                                       measured slower on B200 (profiles/r2_experiments.md), kept as the evidence for that design    */
-#define MM_FLAG_POOL_KERNEL  256u   /* trace with the persistent ray-pool kernel (pool_kernel.cu: warps own a pool of paths in shared
-                                      memory and run interior / leaf / shade bodies on work queues) instead of the default
-                                      one-thread-per-path kernel (render_kernel.cu).  Same bits; measured slower on B200
-                                      (profiles/r2_pool_kernel.md), kept as the evidence for that design                    */
-#define MM_FLAG_NO_ZERO_COPY 128u  /* mm_render / mm_render_async: copy the screen with a DMA transfer even when out_rgba is mapped pinned
-                                      memory the kernel could store into directly (for comparisons)                        */
-#define MM_FLAG_RCP_SLAB     64u   /* opt-in arithmetic variant: slab quotients (b - o) * RN(1/d) instead of the literal
-                                      (b - o) / d of shaders.metal:88-93 — what a fast-math compile of the shader amounts to.
-                                      NOT the default; the oracle implements the same rule under the same flag and the
-                                      kernel matches it bit for bit, but results differ from the literal mode's.       */
 
 /* Exact event counts of one render call; identical on CPU oracle and GPU (SURVEY §8 d). */
 typedef struct mm_counters {
