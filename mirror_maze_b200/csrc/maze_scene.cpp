@@ -10,15 +10,21 @@ namespace mmh {
 
 namespace {
 
-// main.rs:328-352 — parent-pointer forest, no rank, no path compression.
+// main.rs:328-352 — parent-pointer forest.  The reference walks to the root without rank or path compression (minutes of
+// chain walking at n = 256); which node is the root never reaches the output — Kruskal only asks whether two cells are in the
+// same set (main.rs:388) — so the walk halves the path as it goes: the same accept / reject sequence, the same maze.
 struct TreeBuilder {
     std::vector<int64_t> nodes;   // -1 == None
     void new_node() { nodes.push_back(-1); }
-    size_t get_root(size_t index) const {
-        while (nodes[index] >= 0) index = (size_t)nodes[index];
+    size_t get_root(size_t index) {
+        while (nodes[index] >= 0) {
+            const size_t parent = (size_t)nodes[index];
+            if (nodes[parent] >= 0) nodes[index] = nodes[parent];   // path halving
+            index = parent;
+        }
         return index;
     }
-    bool connected(size_t left, size_t right) const { return get_root(left) == get_root(right); }
+    bool connected(size_t left, size_t right) { return get_root(left) == get_root(right); }
     void connect(size_t parent, size_t child) {
         size_t root = get_root(child);
         nodes[root] = (int64_t)parent;
