@@ -713,7 +713,14 @@ def run_flythroughs(a, mm, torch, dist, rank, world, local):
         r.wait_present()
         return rays
 
-    # parity: the first 3 frames of this rank's fly-through against the oracle + the blur model, on a fresh renderer state
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rays = fly(rank, a.frames)
+    dt = time.perf_counter() - t0
+    # parity: the first 3 frames of this rank's fly-through against the oracle + the blur model, on a fresh renderer state —
+    # AFTER the timed run: the oracle's OpenMP workers keep spinning for a while and would steal the cores the frame loop needs
     parity_ok = None
     if not a.no_cpu_baseline:
         from oracle import oracle
@@ -737,17 +744,11 @@ def run_flythroughs(a, mm, torch, dist, rank, world, local):
             model = blur(model)
             ok[0] = ok[0] and model.tobytes() == hf.array.tobytes()
 
-        fly(rank, 3, check)
-        parity_ok = ok[0]
         r.close()
         r = mm.Renderer(local)
         r.upload_scene(sc, noise)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    rays = fly(rank, a.frames)
-    dt = time.perf_counter() - t0
+        fly(rank, 3, check)
+        parity_ok = ok[0]
     tot = np.array([rays, a.frames, dt, 1.0 if parity_ok in (True, None) else 0.0], dtype=np.float64)
     if dist is not None:
         t = torch.tensor(tot, device=f"cuda:{local}")
