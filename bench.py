@@ -596,7 +596,8 @@ def build_roofline(a, r, info, cnt_frame, kernel_mean_ms, world, clocks):
             "kernel": "trace kernel", "kernel_ms": round(kernel_mean_ms, 4),
             "peak_source": f"{info['n_sms']} SMs x 128 FP32 lanes x {sm_max:.0f} MHz (max SM clock); no entry for this bound in MEASURED_PEAKS.json",
             "peak_at_load_clock": round(issue_peak_now, 2), "frac_at_load_clock": round(achieved_tops / issue_peak_now, 4),
-            "peak_measured_ffma": round(ffma_peak, 2), "algorithmic_ops_per_launch": int(ops_per_launch),
+            "peak_measured_ffma": round(ffma_peak, 2), "frac_of_measured_ffma": round(achieved_tops / ffma_peak, 4) if ffma_peak else None,
+            "algorithmic_ops_per_launch": int(ops_per_launch),
             "def": "ALGORITHMIC FP32-pipe operations of the reference's algorithm: 50 per inner visit (2 slab tests x 25, a divide = 1 op) + 84 per "
                    "rect test (SURVEY 8d), from the exact oracle-identical counters, over the kernel's CUDA-event time.  The kernel EXECUTES more: "
                    "each literal divide is an exact 4-instruction sequence",
