@@ -95,6 +95,8 @@ typedef struct mm_params {
                                       texel returns (Metal's float -> unorm8 conversion rounds to nearest even) — so the persistent
                                       screen, the blur that feeds on it (mm_present_rgba8) and the frame hold 8-bit values.  Default is
                                       the unquantised fp32 screen the 1e-3 radiance tolerance is stated on.                       */
+#define MM_FLAG_GENERAL_RECTS 2048u /* use the general rect test even when every rect of the scene is axis-aligned and the collapsed
+                                      axis-aligned test applies (validation; same bits)                                         */
 #define MM_FLAG_REGROUP     1024u   /* trace with trace_kernel_rg: the default kernel plus warp-level ray compaction — at segment boundaries
                                       the block's live paths are re-formed into warps through shared memory, sorted by ray steepness
                                       |dir.y|, ended paths dropped.  Same bits; fewer instructions (-14 % interior-body executions) but
@@ -254,6 +256,7 @@ typedef struct mm_scene_info {
     uint32_t fast_rect_ok;      /* 1 when every edge length allows the divide-free rect edge test      */
     uint32_t fast_slab_ok;      /* 1 when scene bounds allow the shared-reciprocal exact slab test    */
     uint32_t smem_bytes, block_threads, blocks_per_sm, n_sms;
+    uint32_t axis_rects;        /* 1 when every rect is axis-aligned: the collapsed 32-byte rect test is in use */
 } mm_scene_info;
 int mm_get_scene_info(mm_ctx *ctx, mm_scene_info *out);
 
@@ -306,6 +309,15 @@ int mm_selftest_quotient(mm_ctx *ctx, uint64_t n_pairs, uint64_t seed, uint64_t 
  * Host-only, no GPU needed.
  */
 int mm_rect_edge_thresholds(float length, float *lo, float *up);
+/*
+ * Verification hook for the axis-aligned rect test.  For a rect whose normal is +-e_k and whose edges lie along the other two
+ * axes (every wall, floor, roof and light panel of a maze) ray_rect_intersect (shaders.metal:51-67) collapses exactly to
+ * a = RN(RN(origin_k - o_k) / dir_k) and interval tests lo_j <= p_j <= hi_j on the intersection point's in-plane coordinates
+ * p_j = RN(o_j + RN(dir_j * a)); the intervals are found by bisection over the floats with the literal operations.  out[0..5] =
+ * c, lo_a, hi_a, lo_b, hi_b (a < b the in-plane axes), *k = normal axis (3: degenerate rect, never hit).  MM_ERR_UNSUPPORTED
+ * when the rect is not axis-aligned (a scene with such a rect uses the general test throughout).  Host-only.
+ */
+int mm_axis_rect(const mm_plane *plane, float out[5], uint32_t *k);
 
 /* ---- One process, several GPUs (SURVEY §8 b/e) ---------------------------------------------------------------------- */
 

@@ -18,6 +18,7 @@ FLAG_NO_ZERO_COPY = 128
 FLAG_POOL_KERNEL = 256
 FLAG_SCREEN_RGBA8 = 512
 FLAG_REGROUP = 1024
+FLAG_GENERAL_RECTS = 2048
 EXCHANGE_PEER, EXCHANGE_NCCL, EXCHANGE_NONE = 0, 1, 2
 MAX_PEERS = 8
 
@@ -87,7 +88,7 @@ class Debug(C.Structure):
 
 class SceneInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_planes", "n_nodes", "bvh_depth", "max_leaf", "fast_rect_ok", "fast_slab_ok",
-                                          "smem_bytes", "block_threads", "blocks_per_sm", "n_sms")]
+                                          "smem_bytes", "block_threads", "blocks_per_sm", "n_sms", "axis_rects")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -138,6 +139,7 @@ PROTOTYPES = {
     "mm_selftest_quotient": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _P(C.c_uint64)]),
     "mm_render_peers_device": (C.c_int, [_vp, _P(Uniform), _P(Params), _P(C.c_void_p), C.c_uint32]),
     "mm_rect_edge_thresholds": (C.c_int, [C.c_float, _P(C.c_float), _P(C.c_float)]),
+    "mm_axis_rect": (C.c_int, [_P(Plane), _P(C.c_float), _P(C.c_uint32)]),
     "mm_microbench": (C.c_int, [_vp, C.c_int, C.c_uint64, _P(C.c_double)]),
     "mm_present": (C.c_int, [_vp, _vp]),
     "mm_present_rgba8": (C.c_int, [_vp, _vp, _vp]),

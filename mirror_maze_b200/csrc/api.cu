@@ -95,7 +95,7 @@ int mm_destroy(mm_ctx *ctx) {
     if (!ctx) return MM_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_pairs); cudaFree(ctx->d_rects); cudaFree(ctx->d_shade); cudaFree(ctx->d_noise); cudaFree(ctx->d_chunks);
+    cudaFree(ctx->d_pairs); cudaFree(ctx->d_rects); cudaFree(ctx->d_rects_axis); cudaFree(ctx->d_shade); cudaFree(ctx->d_noise); cudaFree(ctx->d_chunks);
     cudaFree(ctx->d_counters); cudaFree(ctx->d_screen); cudaFree(ctx->d_screen2); cudaFree(ctx->d_dbg_rad);
     for (auto p : ctx->d_dbg_u32) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -135,8 +135,8 @@ int mm_upload_scene(mm_ctx *ctx, const mm_plane *planes, uint32_t n_planes, cons
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_scene = false;
-    cudaFree(ctx->d_pairs); cudaFree(ctx->d_rects); cudaFree(ctx->d_shade); cudaFree(ctx->d_noise);
-    ctx->d_pairs = nullptr; ctx->d_rects = nullptr; ctx->d_shade = nullptr; ctx->d_noise = nullptr;
+    cudaFree(ctx->d_pairs); cudaFree(ctx->d_rects); cudaFree(ctx->d_rects_axis); cudaFree(ctx->d_shade); cudaFree(ctx->d_noise);
+    ctx->d_pairs = nullptr; ctx->d_rects = nullptr; ctx->d_rects_axis = nullptr; ctx->d_shade = nullptr; ctx->d_noise = nullptr;
     const size_t noise_bytes = (size_t)noise_w * noise_h * 4;
     {
         // The kernel forms record addresses as {high word, low word + offset} (one 32-bit add, render_kernel.cu), so the
@@ -160,6 +160,10 @@ int mm_upload_scene(mm_ctx *ctx, const mm_plane *planes, uint32_t n_planes, cons
     }
     CK(cudaMalloc(&ctx->d_rects, prep.rects.size() * sizeof(RectI)));
     CK(cudaMalloc(&ctx->d_shade, prep.shade.size() * sizeof(RectS)));
+    if (prep.axis_ok) {
+        CK(cudaMalloc(&ctx->d_rects_axis, prep.rects_axis.size() * sizeof(RectA)));
+        CK(cudaMemcpyAsync(ctx->d_rects_axis, prep.rects_axis.data(), prep.rects_axis.size() * sizeof(RectA), cudaMemcpyHostToDevice, ctx->stream));
+    }
     CK(cudaMalloc(&ctx->d_noise, noise_bytes));
     CK(cudaMemcpyAsync(ctx->d_pairs, prep.pairs.data(), prep.pairs.size() * sizeof(PairRec), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_rects, prep.rects.data(), prep.rects.size() * sizeof(RectI), cudaMemcpyHostToDevice, ctx->stream));
@@ -279,6 +283,7 @@ int build_launch(mm_ctx *ctx, const mm_uniform *uni, const mm_params *par, bool 
     p.rect_fast_ok = (ctx->rect_fast_ok && !(par->flags & MM_FLAG_FORCE_LITERAL)) ? 1u : 0u;
     p.total_paths = (uint64_t)count * T;
     p.pairs = ctx->d_pairs; p.rects = ctx->d_rects; p.shade = ctx->d_shade;
+    p.rects_axis = (p.rect_fast_ok && !(par->flags & MM_FLAG_GENERAL_RECTS)) ? ctx->d_rects_axis : nullptr;
     p.chunks = ctx->d_chunks; p.noise = ctx->d_noise;
     p.counters = ctx->d_counters;
 
@@ -703,6 +708,15 @@ int mm_rect_edge_thresholds(float length, float *lo, float *up) {
     return edge_thresholds(length, lo, up) ? MM_OK : MM_ERR_UNSUPPORTED;
 }
 
+int mm_axis_rect(const mm_plane *plane, float out[5], uint32_t *k) {
+    if (!plane || !out || !k) return MM_ERR_INVALID;
+    RectA r;
+    if (!axis_rect(*plane, &r)) return MM_ERR_UNSUPPORTED;
+    out[0] = r.c; out[1] = r.lo_a; out[2] = r.hi_a; out[3] = r.lo_b; out[4] = r.hi_b;
+    *k = r.k;
+    return MM_OK;
+}
+
 int mm_selftest_quotient(mm_ctx *ctx, uint64_t n_pairs, uint64_t seed, uint64_t *mismatches) {
     if (!ctx || !mismatches) return MM_ERR_INVALID;
     ctx->err.clear();
@@ -744,6 +758,7 @@ int mm_get_scene_info(mm_ctx *ctx, mm_scene_info *out) {
     if (!ctx->have_scene) return fail(ctx, MM_ERR_NO_SCENE, "no scene uploaded");
     out->n_planes = ctx->n_slots; out->n_nodes = ctx->n_nodes; out->bvh_depth = ctx->depth; out->max_leaf = ctx->max_leaf;
     out->fast_rect_ok = ctx->rect_fast_ok ? 1u : 0u;
+    out->axis_rects = ctx->d_rects_axis ? 1u : 0u;
     out->fast_slab_ok = ctx->fast_ok ? 1u : 0u;
     out->smem_bytes = ctx->last_smem; out->block_threads = ctx->last_block_threads; out->blocks_per_sm = ctx->last_blocks_per_sm;
     out->n_sms = (uint32_t)ctx->n_sms;

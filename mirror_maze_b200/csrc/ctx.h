@@ -18,6 +18,7 @@ struct mm_ctx {
     mmk::PairRec *d_pairs = nullptr;
     mmk::RectI *d_rects = nullptr;
     mmk::RectS *d_shade = nullptr;
+    mmk::RectA *d_rects_axis = nullptr;   // present when every rect is axis-aligned
     uint8_t *d_noise = nullptr;
     uint32_t n_pairs = 0, n_slots = 0, n_nodes = 0, root_link = 0, root_count = 0, depth = 0, max_leaf = 0, noise_w = 0, noise_h = 0;
     bool fast_ok = false, rect_fast_ok = false;

@@ -40,6 +40,22 @@ struct __align__(16) RectI {
 };
 static_assert(sizeof(RectI) == 64, "rect is 64 B");
 
+// The same rectangle for scenes whose rects are all axis-aligned (every maze is: walls, floor, roof, light panels), 32 B.
+// With n = +-e_k the literal test collapses exactly: dot(dir, n) = +-dir_k and dot(origin - o, n) = +-RN(c - o_k) (the other
+// products are +-0), so a = RN(RN(c - o_k) / dir_k) bit for bit; and with v, u along the other two axes the edge tests
+// lo <= RN(RN(p_j - origin_j) * edge_j) <= up are monotone in the intersection point's coordinate p_j = RN(o_j + RN(dir_j * a)),
+// i.e. an interval [lo_j, hi_j] on p_j itself, found at upload by bisection over the floats with the literal operations
+// (scene_prep.cpp::axis_rect).  Whenever the literal test can accept (0.1 < a < t <= 1e30, all terms finite) both forms decide
+// alike; whenever it cannot, neither accepts.  a, b = the two in-plane axes in increasing order.
+struct __align__(32) RectA {
+    float c;                 // plane coordinate origin[k]
+    float lo_a, hi_a, lo_b;
+    float hi_b;
+    uint32_t k;              // normal axis 0 / 1 / 2; 3 = never hit (degenerate rect: zero-length edge, NaN normal)
+    uint32_t pad[2];
+};
+static_assert(sizeof(RectA) == 32, "axis-aligned rect is 32 B");
+
 // Shading constants per slot, 32 B: albedo and emissions.rgb * emissions.a (shaders.metal:312,314,327).
 struct __align__(16) RectS {
     float4 color;    // rgb, bits = material (0 matte, 1 mirror)
@@ -73,6 +89,7 @@ struct KParams {
     uint64_t total_paths;
     const PairRec *pairs;
     const RectI *rects;
+    const RectA *rects_axis;          // non-null when every rect of the scene is axis-aligned (and MM_FLAG_FORCE_LITERAL is off)
     const RectS *shade;
     const mm_chunk *chunks;
     const uint8_t *noise;

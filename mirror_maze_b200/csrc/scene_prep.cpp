@@ -3,6 +3,7 @@
 // with -ffp-contract=off: the per-rect constants are computed with exactly the operations ray_rect_intersect
 // performs per call (shaders.metal:52,60-61: normalize(cross(v,u)), length(v), length(u)) and the shader performs
 // per hit (:312 emissions.rgb * emissions.a), one IEEE rounding each, so the kernel sees the literal values.
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include "scene_prep.h"
@@ -43,6 +44,95 @@ bool edge_thresholds(float L, float *lo, float *up) {
     const double tl = T - (double)th;                             // exact
     *up = (tl > 0.0 || (tl == 0.0 && (bits & 1u) == 0u)) ? th : std::nextafterf(th, -INFINITY);
     *lo = -(float)(std::floor((double)L * 0.5) * 1.401298464324817e-45 /*2^-149*/);
+    return true;
+}
+
+namespace {
+// floats in their total order as integers (finite values and infinities; NaN never gets here)
+inline int64_t fkey(float f) {
+    uint32_t b; std::memcpy(&b, &f, 4);
+    return (b & 0x80000000u) ? -(int64_t)(b & 0x7FFFFFFFu) : (int64_t)b;      // -0 and +0 share key 0
+}
+inline float fkey_inv(int64_t k) {
+    const uint32_t b = k >= 0 ? (uint32_t)k : ((uint32_t)(-k) | 0x80000000u);
+    float f; std::memcpy(&f, &b, 4); return f;
+}
+// The edge test as the literal code evaluates it for an in-plane coordinate p of the intersection point:
+// x = RN(RN(p - origin_j) * edge_j), accepted iff lo <= x <= up (the interval form of 0 <= RN(x / L) <= L, edge_thresholds).
+inline bool edge_accepts(float p, float origin_j, float edge_j, float lo, float up) {
+    const float rv = p - origin_j;
+    const float x = rv * edge_j;
+    return lo <= x && x <= up;
+}
+// Interval [lo_p, hi_p] of floats p with edge_accepts(p): the test is a monotone chain (p -> p - origin_j -> * edge_j) followed
+// by an interval, so the accepted set is contiguous; its ends are found by bisection over the float order from one accepted
+// point.  Returns false when no float is accepted.
+bool edge_interval(float origin_j, float edge_j, float lo, float up, float *lo_p, float *hi_p) {
+    if (!(lo <= up) || edge_j == 0.0f) return false;
+    // a point inside: the middle of the edge, then its neighbourhood, then the ends
+    const float cand[5] = {origin_j + 0.5f * edge_j, origin_j, origin_j + edge_j, origin_j + 0.25f * edge_j, origin_j + 0.75f * edge_j};
+    float seed = 0.0f;
+    bool found = false;
+    for (float c : cand)
+        if (edge_accepts(c, origin_j, edge_j, lo, up)) { seed = c; found = true; break; }
+    if (!found) return false;
+    const int64_t ks = fkey(seed);
+    int64_t a = fkey(-3.4028234663852886e38f), b = ks;          // lowest accepted: first key in [a, ks] that accepts
+    while (a < b) {
+        const int64_t m = a + (b - a) / 2;
+        if (edge_accepts(fkey_inv(m), origin_j, edge_j, lo, up)) b = m; else a = m + 1;
+    }
+    *lo_p = fkey_inv(a);
+    a = ks; b = fkey(3.4028234663852886e38f);                   // highest accepted: last key in [ks, b] that accepts
+    while (a < b) {
+        const int64_t m = a + (b - a + 1) / 2;
+        if (edge_accepts(fkey_inv(m), origin_j, edge_j, lo, up)) a = m; else b = m - 1;
+    }
+    *hi_p = fkey_inv(a);
+    return true;
+}
+inline int single_axis(const mm_float3 &v) {       // index of the only non-zero component, or -1
+    const float c[3] = {v.x, v.y, v.z};
+    int k = -1;
+    for (int i = 0; i < 3; i++)
+        if (c[i] != 0.0f) { if (k >= 0) return -1; k = i; }
+    return k;
+}
+}  // namespace
+
+bool axis_rect(const mm_plane &m, RectA *out) {
+    RectA r;
+    std::memset(&r, 0, sizeof(r));
+    const float nan = std::nanf("");
+    const float v[3] = {m.v.x, m.v.y, m.v.z}, u[3] = {m.u.x, m.u.y, m.u.z}, o[3] = {m.origin.x, m.origin.y, m.origin.z};
+    for (int i = 0; i < 3; i++)
+        if (!std::isfinite(v[i]) || !std::isfinite(u[i]) || !std::isfinite(o[i])) return false;
+    const int jv = single_axis(m.v), ju = single_axis(m.u);
+    const bool v_zero = v[0] == 0.0f && v[1] == 0.0f && v[2] == 0.0f, u_zero = u[0] == 0.0f && u[1] == 0.0f && u[2] == 0.0f;
+    if (v_zero || u_zero) {                         // zero-length edge: cross = 0, normal = NaN, the literal test never accepts
+        r.c = nan; r.lo_a = r.lo_b = nan; r.hi_a = r.hi_b = nan; r.k = 3u;
+        *out = r;
+        return true;
+    }
+    if (jv < 0 || ju < 0 || jv == ju) return false;
+    const int k = 3 - jv - ju;                      // normal axis
+    // the normal must come out as exactly +-e_k: normalize(cross(v, u)) with the operations of the upload / the shader
+    const float c3[3] = {v[1] * u[2] - v[2] * u[1], v[2] * u[0] - v[0] * u[2], v[0] * u[1] - v[1] * u[0]};
+    const float lc = std::sqrt(dot3(c3, c3));
+    const float n[3] = {c3[0] / lc, c3[1] / lc, c3[2] / lc};
+    for (int i = 0; i < 3; i++)
+        if (!(i == k ? (n[i] == 1.0f || n[i] == -1.0f) : n[i] == 0.0f)) return false;
+    const float lv = std::sqrt(dot3(v, v)), lu = std::sqrt(dot3(u, u));
+    float lo_v, up_v, lo_u, up_u;
+    if (!edge_thresholds(lv, &lo_v, &up_v) || !edge_thresholds(lu, &lo_u, &up_u)) return false;
+    const int a = k == 0 ? 1 : 0, b = k == 2 ? 1 : 2;           // in-plane axes in increasing order
+    float lo[3], hi[3];
+    const bool okv = edge_interval(o[jv], v[jv], lo_v, up_v, &lo[jv], &hi[jv]);
+    const bool oku = edge_interval(o[ju], u[ju], lo_u, up_u, &lo[ju], &hi[ju]);
+    r.c = o[k]; r.k = (uint32_t)k;
+    if (!okv || !oku) { r.c = nan; r.lo_a = r.lo_b = nan; r.hi_a = r.hi_b = nan; r.k = 3u; *out = r; return true; }   // nothing ever accepted
+    r.lo_a = lo[a]; r.hi_a = hi[a]; r.lo_b = lo[b]; r.hi_b = hi[b];
+    *out = r;
     return true;
 }
 
@@ -131,6 +221,12 @@ int prepare_scene(const mm_plane *planes, uint32_t n_planes, const mm_bvh_node *
         sh.emitted = make_float4(e.x * e.w, e.y * e.w, e.z * e.w, as_float(id));
     }
     out.rect_fast_ok = rect_fast_ok;
+    // axis-aligned form (every rect of a maze scene): used by the kernel's leaf test when ALL rects have it
+    out.rects_axis.resize(n_planes);
+    bool axis_ok = rect_fast_ok;
+    for (uint32_t s = 0; s < n_planes && axis_ok; s++) axis_ok = axis_rect(planes[indices[s]], &out.rects_axis[s]);
+    if (!axis_ok) out.rects_axis.clear();
+    out.axis_ok = axis_ok;
     return MM_OK;
 }
 

@@ -234,6 +234,34 @@ __device__ __forceinline__ void leaf_step(const RectI *__restrict__ rects, V3 or
     cur = *--sp;
 }
 
+// One leaf visit for scenes whose rects are all axis-aligned (render_kernel.cuh, RectA): the literal test of
+// shaders.metal:51-67 collapsed to one subtraction, one IEEE divide, two multiply-adds and interval tests on the intersection
+// point's two in-plane coordinates — the same accept / reject decisions and the same beam.t, bit for bit (see RectA).
+template <bool CNT>
+__device__ __forceinline__ void leaf_step_axis(const RectA *__restrict__ rects, V3 ori, V3 dir, float &t, uint32_t &slot, uint32_t &cur,
+                                               uint32_t *&sp, Tally &tl) {
+    const uint32_t first = cur & 0xFFFFFFu, count = (cur >> 24) & 0x7Fu;
+#pragma unroll 1
+    for (uint32_t i = 0; i < count; i++) {
+        const Line32 q = ldg256(rects + first + i);
+        if (CNT) tl.rect++;
+        const float c = lo2f(q.x), lo_a = hi2f(q.x), hi_a = lo2f(q.y), lo_b = hi2f(q.y), hi_b = lo2f(q.z);
+        const uint32_t k = __float_as_uint(hi2f(q.z));
+        const bool k0 = k == 0u, k2 = k == 2u;
+        const float o_k = k0 ? ori.x : (k2 ? ori.z : ori.y), d_k = k0 ? dir.x : (k2 ? dir.z : dir.y);
+        const float o_a = k0 ? ori.y : ori.x, d_a = k0 ? dir.y : dir.x;       // in-plane axes in increasing order
+        const float o_b = k2 ? ori.y : ori.z, d_b = k2 ? dir.y : dir.z;
+        const float a = fdiv(fsub(c, o_k), d_k);                                 // :53-55 with n = +-e_k
+        const float pa = fadd(o_a, fmul(d_a, a)), pb = fadd(o_b, fmul(d_b, a));  // :56, the two in-plane coordinates
+        const bool inside = (lo_a <= pa) & (pa <= hi_a) & (lo_b <= pb) & (pb <= hi_b);   // :58-63 as intervals on the point itself
+        if (inside && d_k != 0.0f && a > 0.1f && a < t) {                        // :63
+            t = a;
+            slot = first + i;
+        }
+    }
+    cur = *--sp;
+}
+
 // intersect_bvh_iterative (shaders.metal:115-156) for the rays of one warp.  Every lane of the warp calls this together
 // (lanes without a ray pass alive = false) and the warp votes on which body to execute: the interior body runs (kInnerReps
 // visits per vote) while the lanes standing at an interior node outweigh the lanes waiting at a leaf
@@ -256,8 +284,9 @@ constexpr int kRepUnroll = 2;                      // visits per loop trip: 2 me
 // radiance, RNG state, counters, pixel bookkeeping) in the caller's frame, so the traversal loop has the whole 64-register
 // budget for its per-ray constants.
 struct Hit { float t; uint32_t slot; };
-template <bool MIXED, bool CNT, bool RCP>
-__device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const RectI *__restrict__ rects, uint32_t root, bool alive,
+// AX = true: the scene's rects are all axis-aligned and `rects` points at RectA records (leaf_step_axis).
+template <bool MIXED, bool CNT, bool RCP, bool AX = false>
+__device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const void *__restrict__ rects, uint32_t root, bool alive,
                                      bool lit, V3 ori, V3 dir, float beam_t, uint32_t beam_slot, Tally *tlp) {
     Tally tl = {0u, 0u, 0u, 0u};
     uint32_t stack[MM_MAX_STACK];              // local memory (L1); BVH depth is validated against it at upload
@@ -319,7 +348,8 @@ __device__ __noinline__ Hit traverse(const PairRec *__restrict__ pairs, const Re
         } else {
             if (isL) {
                 if (CNT) tl.leaf++;
-                leaf_step<CNT, MIXED>(rects, ori, dir, t, slot, cur, sp, tl);
+                if (AX) leaf_step_axis<CNT>(static_cast<const RectA *>(rects), ori, dir, t, slot, cur, sp, tl);
+                else leaf_step<CNT, MIXED>(static_cast<const RectI *>(rects), ori, dir, t, slot, cur, sp, tl);
             }
         }
     }

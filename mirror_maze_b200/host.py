@@ -170,6 +170,18 @@ def check_collision(nodes, bmin, bmax):
                                                      Float3(*[float(v) for v in bmax])))
 
 
+def axis_rect(plane):
+    """The axis-aligned form of one rect (mm_axis_rect): (c, lo_a, hi_a, lo_b, hi_b, k) or None when it is not axis-aligned."""
+    import ctypes as C
+    rec = np.ascontiguousarray(plane, dtype=PLANE_DTYPE).reshape(1)
+    out, k = (C.c_float * 5)(), C.c_uint32()
+    rc = abi.load_library().mm_axis_rect(rec.ctypes.data_as(C.POINTER(abi.Plane)), out, C.byref(k))
+    if rc == -5:
+        return None
+    _check(rc, "mm_axis_rect")
+    return tuple(np.float32(v) for v in out) + (int(k.value),)
+
+
 def rect_edge_thresholds(length):
     """Interval [lo, up] on x = dot(rv, edge) equivalent to `0 <= RN(x / length) <= length` (mm_rect_edge_thresholds);
     None when the length is outside the guarded range."""

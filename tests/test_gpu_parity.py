@@ -60,13 +60,16 @@ def test_cuda_matches_committed_golden(mm, noise, scenes, renderer, name):
         assert cnt[k] == v, k
 
 
-@pytest.mark.parametrize("flags_name", ["literal", "counters_only", "literal_counters", "regroup", "regroup_literal", "regroup_counters"])
+@pytest.mark.parametrize("flags_name", ["literal", "counters_only", "literal_counters", "regroup", "regroup_literal", "regroup_counters", "general_rects",
+                                        "general_rects_counters"])
 @pytest.mark.parametrize("name", ["cfg1", "cfg2_small", "maze64", "ref_dispatch", "chunk5_spp32", "chunk1_spp256", "mirror_limit2", "bounce0", "ragged"])
 def test_every_kernel_variant_is_bit_identical(mm, oracle, noise, scenes, renderer, name, flags_name):
     # "regroup" = MM_FLAG_REGROUP: trace_kernel_rg, the default kernel plus warp-level ray compaction at segment boundaries
     flags = {"literal": mm.FLAG_FORCE_LITERAL, "counters_only": mm.FLAG_COUNTERS,
              "literal_counters": mm.FLAG_FORCE_LITERAL | mm.FLAG_COUNTERS, "regroup": mm.FLAG_REGROUP,
-             "regroup_literal": mm.FLAG_REGROUP | mm.FLAG_FORCE_LITERAL, "regroup_counters": mm.FLAG_REGROUP | mm.FLAG_COUNTERS}[flags_name]
+             "regroup_literal": mm.FLAG_REGROUP | mm.FLAG_FORCE_LITERAL, "regroup_counters": mm.FLAG_REGROUP | mm.FLAG_COUNTERS,
+             # the default leaf test is the collapsed axis-aligned one (every maze rect is axis-aligned); this is the general one
+             "general_rects": mm.FLAG_GENERAL_RECTS, "general_rects_counters": mm.FLAG_GENERAL_RECTS | mm.FLAG_COUNTERS}[flags_name]
     sc, u, p, ch = build_case(mm, name, scenes)
     renderer.upload_scene(sc, noise)
     ref = oracle.render(sc, noise, u, p, ch, debug=True)

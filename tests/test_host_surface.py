@@ -219,3 +219,75 @@ def test_reference_arm_inputs_equal_the_products(mm):
     assert np.ascontiguousarray(ref["nodes"]).tobytes() == np.ascontiguousarray(sc.nodes).tobytes()
     assert np.array_equal(ref["indices"], sc.indices) and np.array_equal(ref["materials"], sc.materials)
     assert np.ascontiguousarray(ref["emissions"], dtype=np.float32).tobytes() == np.ascontiguousarray(sc.emissions, dtype=np.float32).tobytes()
+
+
+def test_axis_aligned_rect_test_decides_like_the_literal_one(mm, oracle):
+    """mm_axis_rect: for axis-aligned rects the kernel evaluates a = RN(RN(c - o_k) / d_k) and interval tests on the intersection
+    point's in-plane coordinates instead of ray_rect_intersect (shaders.metal:51-67).  Checked against the oracle's literal
+    function: random rays, rays aimed within a few ulps of every rect border, rays from points on the rect's plane, zero
+    direction components; every wall / floor / roof / panel shape of the mazes plus odd sizes, both windings, all three axes."""
+    from mirror_maze_b200.host import PLANE_DTYPE
+
+    F = np.float32
+    rng = np.random.default_rng(7)
+
+    def collapsed(rec, o, d, t):
+        c, lo_a, hi_a, lo_b, hi_b, k = rec
+        if k == 3:
+            return False, t
+        a_ax, b_ax = (1 if k == 0 else 0), (1 if k == 2 else 2)
+        with np.errstate(all="ignore"):
+            a = F(F(c - o[k]) / d[k])
+            pa = F(o[a_ax] + F(d[a_ax] * a)); pb = F(o[b_ax] + F(d[b_ax] * a))
+        hit = bool(lo_a <= pa <= hi_a and lo_b <= pb <= hi_b and d[k] != 0 and a > F(0.1) and a < t)
+        return hit, (float(a) if hit else t)
+
+    shapes = [((-50.0, 2.0, -30.0), (0, 0, 20.0), (0, -10.0, 0)), ((-50.0, 2.0, -30.0), (30.0, 0, 0), (0, -10.0, 0)),
+              ((-160.0, 2.0, -160.0), (320.0, 0, 0), (0, 0, 320.0)), ((-160.0, -8.0, -160.0), (0, 0, 320.0), (320.0, 0, 0)),
+              ((-4.95, 1.0, -49.9), (9.9, 0, 0), (0, -6.0, 0)), ((12.5, 0.37, 3.1), (0, 0, -7.3), (0, 1.9, 0)),
+              ((0.0, 2.0, 0.0), (0, 0, 10.0), (0, -10.0, 0)), ((1280.0, 2.0, -1270.0), (0, -10.0, 0), (-1e-3, 0, 0))]
+    checked = hits = 0
+    for origin, v, u in shapes:
+        P = np.zeros(1, dtype=PLANE_DTYPE)
+        P[0]["origin"], P[0]["v"], P[0]["u"], P[0]["color"] = origin, v, u, (0.5, 0.5, 0.5)
+        rec = mm.axis_rect(P[0])
+        assert rec is not None and rec[5] in (0, 1, 2)
+        k = rec[5]
+        org, vv, uu = np.array(origin, F), np.array(v, F), np.array(u, F)
+        targets = []
+        for sv in (0.0, 1.0, 0.5, 0.25):                       # points on / around the borders and inside
+            for su in (0.0, 1.0, 0.5, 0.75):
+                base = org + F(sv) * vv + F(su) * uu
+                for _ in range(6):
+                    jit = base.copy()
+                    for j in range(3):
+                        jit[j] = np.nextafter(jit[j], F(np.inf if rng.random() < 0.5 else -np.inf)) if rng.random() < 0.7 else jit[j]
+                        if rng.random() < 0.3:
+                            jit[j] = F(jit[j] + F(rng.normal() * 1e-5 * max(1.0, abs(float(jit[j])))))
+                    targets.append(jit)
+        for tgt in targets:
+            for _ in range(5):
+                o = (tgt + rng.normal(size=3).astype(F) * F(rng.choice([0.3, 5.0, 80.0]))).astype(F)
+                if rng.random() < 0.15:
+                    o[k] = org[k]                               # ray origin on the rect's plane
+                d = (tgt - o).astype(F)
+                n = F(np.sqrt(float(d @ d))) or F(1.0)
+                d = (d / n).astype(F) if rng.random() < 0.8 else d
+                if rng.random() < 0.1:
+                    d[int(rng.integers(0, 3))] = F(0.0)
+                for t in (F(1e30), F(rng.uniform(0.05, 200.0))):
+                    lit = oracle.ray_rect(o, d, float(t), P[0])
+                    col = collapsed(rec, o, d, t)
+                    assert lit[0] == col[0] and (not lit[0] or np.float32(lit[1]) == np.float32(col[1])), (origin, v, u, o, d, t, lit, col)
+                    checked += 1
+                    hits += int(lit[0])
+    assert checked > 7000 and checked // 10 < hits < checked - checked // 10          # both outcomes, plentifully
+    # degenerate rects (zero-length walls, main.rs:416,437) never hit in either form; tilted rects are refused
+    Z = np.zeros(1, dtype=PLANE_DTYPE); Z[0]["origin"], Z[0]["v"], Z[0]["u"] = (1, 2, 3), (0, 0, 0), (0, -10, 0)
+    assert mm.axis_rect(Z[0])[5] == 3
+    T = np.zeros(1, dtype=PLANE_DTYPE); T[0]["origin"], T[0]["v"], T[0]["u"] = (1, 2, 3), (1, 0, 1), (0, -10, 0)
+    assert mm.axis_rect(T[0]) is None
+    # every rect of the mazes has the axis-aligned form
+    for n_maze in (10, 32):
+        sc = mm.MazeScene(n_maze, 0)
+        assert all(mm.axis_rect(pl) is not None for pl in sc.planes)

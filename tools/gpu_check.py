@@ -40,7 +40,7 @@ def main():
         ch = mm.gen_chunks(W, H, 4)
         p = mm.full_frame_params(u, spp=spp, bounce_limit=b)
         ref = oracle.render(sc, noise, u, p, ch, debug=True)
-        for name, flags in (("fast", 0), ("regroup", mm.FLAG_REGROUP), ("literal", mm.FLAG_FORCE_LITERAL)):
+        for name, flags in (("fast", 0), ("general rects", mm.FLAG_GENERAL_RECTS), ("literal", mm.FLAG_FORCE_LITERAL)):
             p.flags = flags
             got = r.render(u, p, ch, debug=True)
             allok &= compare(f"N={n} {W}x{H} spp={spp} b={b} [{name}]", got, ref)
@@ -51,7 +51,7 @@ def main():
         r.upload_scene(sc, noise)
         u = mm.default_uniform(n, 1920, 1080, 4)
         ch = mm.gen_chunks(1920, 1080, 4)
-        for name, flags in (("fast", 0), ("regroup", mm.FLAG_REGROUP), ("literal", mm.FLAG_FORCE_LITERAL), ("rcp", mm.FLAG_RCP_SLAB),
+        for name, flags in (("fast", 0), ("general rects", mm.FLAG_GENERAL_RECTS), ("literal", mm.FLAG_FORCE_LITERAL), ("rcp", mm.FLAG_RCP_SLAB),
                             ("rcp regroup", mm.FLAG_RCP_SLAB | mm.FLAG_REGROUP), ("fast+counters", mm.FLAG_COUNTERS)):
             p = mm.full_frame_params(u, spp=16, bounce_limit=8, flags=flags)
             for it in range(3):
