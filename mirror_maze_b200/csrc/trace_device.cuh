@@ -270,9 +270,9 @@ __device__ __forceinline__ void leaf_step_axis(const RectA *__restrict__ rects, 
 // loop — all lanes descend to a leaf, then all test — left 12 of 32 lanes active in the interior body; see profiles/.)
 // `lit` lanes (operands outside the guarded ranges, or MM_FLAG_FORCE_LITERAL) use the general slab form.
 #ifndef MM_LEAF_WEIGHT
-#define MM_LEAF_WEIGHT 6
+#define MM_LEAF_WEIGHT 8
 #endif
-constexpr uint32_t kLeafWeight = MM_LEAF_WEIGHT;   // measured best on B200 (profiles/r1_sched_sweep.txt)
+constexpr uint32_t kLeafWeight = MM_LEAF_WEIGHT;   // measured best on B200 (r1: 6; 8 since the axis-aligned leaf test made the leaf body cheaper)
 #ifndef MM_INNER_REPS
 #define MM_INNER_REPS 4
 #endif
