@@ -77,6 +77,8 @@ def parse_args():
                     help="N > 1: fused peer/multicast stores from the render kernel, or NCCL all-gather + scatter")
     ap.add_argument("--flags", type=int, default=0, help="MM_FLAG_* for experiments (2 = literal divides for every ray, 64 = reciprocal-multiply slab arithmetic)")
     ap.add_argument("--frames", type=int, default=120, help="cfg5: frames per fly-through")
+    ap.add_argument("--screen", default="f32", choices=["f32", "rgba8"],
+                    help="cfg5: fp32 screen and frames (default), or the reference's RGBA8Unorm screen: quantised stores, 4-byte texels read back")
     a = ap.parse_args()
     w = WORKLOADS[a.workload]
     for k in ("maze", "width", "height", "spp", "bounces"):
@@ -679,9 +681,12 @@ def run_flythroughs(a, mm, torch, dist, rank, world, local):
     gx = max(1, int(math.sqrt(per_frame * a.width / a.height)))
     while per_frame % gx:
         gx -= 1
-    p = mm.Params(spp=a.spp, bounce_limit=a.bounces, mirror_limit=a.mirror_limit, grid_x=gx, grid_y=per_frame // gx)
-    hf = mm.HostFrame(a.height, a.width)
+    rgba8 = a.screen == "rgba8"
+    p = mm.Params(spp=a.spp, bounce_limit=a.bounces, mirror_limit=a.mirror_limit, grid_x=gx, grid_y=per_frame // gx,
+                  flags=mm.FLAG_SCREEN_RGBA8 if rgba8 else 0)
+    hf = mm.HostFrame(a.height, a.width)            # fp32 frames; in the rgba8 mode their first quarter holds the texel bytes
     hf2 = mm.HostFrame(a.height, a.width)
+    texels = np.zeros((a.height, a.width, 4), dtype=np.uint8)
 
     def fly(seed, frames, check=None):
         bag = mm.ChunkBag(a.width, a.height, 4, seed=1000 + seed)
@@ -705,8 +710,13 @@ def run_flythroughs(a, mm, torch, dist, rank, world, local):
             ch = bag.next(per_frame)
             rays += r.render_into(uu, p, ch.ctypes.data, len(ch), None)["rays"]   # compute pass into the persistent screen
             if check is not None:
-                r.present(hf.array)                                             # present pass (blur) + read-back, synchronous
+                if rgba8:
+                    r.present_rgba8(hf.array, texels)                           # quantising blur; float frame and texel bytes
+                else:
+                    r.present(hf.array)                                         # present pass (blur) + read-back, synchronous
                 check(f, uu, ch)
+            elif rgba8:
+                r.present_async_rgba8((hf if f & 1 else hf2).ptr)               # 4 bytes per pixel back to the host
             else:
                 # present pass without the wait (main.rs:888-894): the frame's read-back overlaps the next frame's dispatch;
                 # two pinned host frames alternate
@@ -743,6 +753,10 @@ def run_flythroughs(a, mm, torch, dist, rank, world, local):
             q = mm.Params.from_buffer_copy(bytes(p))
             oracle.render(sc, noise, uu, q, ch, out=model)
             model = blur(model)
+            if rgba8:
+                from oracle import np_oracle
+                model = np_oracle.quant8(model)
+                ok[0] = ok[0] and np.array_equal(texels, np.rint(model * np.float32(255.0)).astype(np.uint8))
             ok[0] = ok[0] and model.tobytes() == hf.array.tobytes()
 
         r.close()
@@ -769,7 +783,9 @@ def run_flythroughs(a, mm, torch, dist, rank, world, local):
                                      "workload_id": "cfg5", "parallelism": "one fly-through per GPU, no exchange until the final collect"},
                           "Mrays_per_s": round(tot[0] / tot[2] / 1e6, 1), "parity_ok": bool(tot[3] == 1.0) if parity_ok is not None else None,
                           "parity": "first 3 frames of every rank's fly-through == oracle render + blur model, bit for bit",
-                          "e2e": {"value": round(tot[1] / tot[2], 2), "unit": "frames/s", "h2d_bytes_per_step": per_frame * 8 + 92, "d2h_bytes_per_step": a.width * a.height * 16},
+                          "screen": "RGBA8Unorm like the reference's (main.rs:702-709): quantised stores, texel bytes read back" if rgba8 else "fp32",
+                          "e2e": {"value": round(tot[1] / tot[2], 2), "unit": "frames/s", "h2d_bytes_per_step": per_frame * 8 + 92,
+                                  "d2h_bytes_per_step": a.width * a.height * (4 if rgba8 else 16)},
                           "gpu_launches": int(2 * a.frames)}), flush=True)
     return 0
 

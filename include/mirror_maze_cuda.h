@@ -280,6 +280,10 @@ int mm_present_rgba8(mm_ctx *ctx, float *out_rgba, uint8_t *out_rgba8);
  * host memory (mm_host_alloc / mm_host_register) and stay untouched until mm_wait_present returns; a later mm_present_async
  * into another buffer queues behind it. */
 int mm_present_async(mm_ctx *ctx, float *out_rgba);
+/* The same on an RGBA8Unorm screen (MM_FLAG_SCREEN_RGBA8 dispatches): the blur's quantised result is the new screen and its
+ * texels — 4 bytes per pixel, what the reference's drawable holds (main.rs:702-709, 888-893) — are read back into pinned
+ * out_rgba8 (H*W*4 bytes) on the second stream. */
+int mm_present_async_rgba8(mm_ctx *ctx, uint8_t *out_rgba8);
 int mm_wait_present(mm_ctx *ctx);
 int mm_present_blur_device(mm_ctx *ctx, const float *d_src, float *d_dst, uint32_t width, uint32_t height);
 

@@ -144,6 +144,7 @@ PROTOTYPES = {
     "mm_present": (C.c_int, [_vp, _vp]),
     "mm_present_rgba8": (C.c_int, [_vp, _vp, _vp]),
     "mm_present_async": (C.c_int, [_vp, _vp]),
+    "mm_present_async_rgba8": (C.c_int, [_vp, _vp]),
     "mm_wait_present": (C.c_int, [_vp]),
     "mm_present_blur_device": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32]),
     "mm_move_camera": (C.c_int, [_vp, C.c_uint32, Float3, Float4, _vp, C.c_uint32, C.c_float, _P(Float3)]),

@@ -635,6 +635,32 @@ int mm_wait_present(mm_ctx *ctx) {
     return MM_OK;
 }
 
+int mm_present_async_rgba8(mm_ctx *ctx, uint8_t *out_rgba8) {
+    if (!ctx) return MM_ERR_INVALID;
+    ctx->err.clear();
+    if (!ctx->d_screen) return fail(ctx, MM_ERR_INVALID, "mm_present_async_rgba8: nothing rendered yet");
+    const size_t n_px = (size_t)ctx->screen_w * ctx->screen_h, bytes = n_px * 4 * sizeof(float);
+    if (!out_rgba8 || !host_device_alias(out_rgba8, n_px * 4))
+        return fail(ctx, MM_ERR_INVALID, "mm_present_async_rgba8: out_rgba8 must be pinned host memory (mm_host_alloc / mm_host_register)");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_snap, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+    }
+    if (!ctx->d_screen2) CK(cudaMalloc(&ctx->d_screen2, bytes));
+    if (!ctx->d_screen8) CK(cudaMalloc(&ctx->d_screen8, n_px * 4));
+    if (ctx->present_in_flight) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));       // the previous texels have left the device
+    CK(launch_blur(ctx->d_screen, ctx->d_screen2, ctx->screen_w, ctx->screen_h, ctx->stream, true, ctx->d_screen8));
+    float *t = ctx->d_screen; ctx->d_screen = ctx->d_screen2; ctx->d_screen2 = t;   // the blurred, quantised image is the screen now
+    CK(cudaEventRecord(ctx->ev_snap, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_snap, 0));
+    CK(cudaMemcpyAsync(out_rgba8, ctx->d_screen8, n_px * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));   // the texel buffer is not the screen: no snapshot
+    CK(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    ctx->present_in_flight = true;
+    return MM_OK;
+}
+
 int mm_present_async(mm_ctx *ctx, float *out_rgba) {
     if (!ctx) return MM_ERR_INVALID;
     ctx->err.clear();

@@ -202,6 +202,10 @@ class Renderer:
         """mm_present_async: blur + read-back into pinned host memory on a second stream; returns at once."""
         self._ck(self._lib.mm_present_async(self._ctx, out_ptr))
 
+    def present_async_rgba8(self, out_ptr):
+        """mm_present_async_rgba8: the quantising blur; the texels (4 bytes per pixel) are read back on a second stream."""
+        self._ck(self._lib.mm_present_async_rgba8(self._ctx, out_ptr))
+
     def wait_present(self):
         self._ck(self._lib.mm_wait_present(self._ctx))
 

@@ -109,8 +109,10 @@ def test_headless_driver_fails_loudly_without_gpu(mm):
 def test_packed_fp32_instruction_mix_shows_no_contraction():
     """ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 regardless of the rounding modifiers (docs/exact_quotient.md),
     which would round once where the contract rounds twice.  The slab sequence is add, mul, fma, fma, fma per quotient pair
-    (add, mul in the reciprocal-multiply mode), six pairs per visit: over all instantiations the SASS must hold exactly
-    FADD2 : FMUL2 : FFMA2 = 2 : 2 : 3.  A fused or dropped instruction changes the ratio."""
+    (add, mul in the reciprocal-multiply mode), six pairs per visit, two unrolled visits per traversal instantiation.  Every
+    trace kernel holds the exact traversal in 3 instantiations (plain, mixed-literal, axis-aligned rects; trace_kernel_rg: 2)
+    and the reciprocal-multiply one in 2, so its SASS must hold exactly FADD2 : FMUL2 : FFMA2 = 60 : 60 : 108 (48 : 48 : 72).
+    A fused or dropped instruction changes the counts."""
     import shutil
     import subprocess
     obj = os.path.join(ROOT, "mirror_maze_b200", "build", "render_kernel.o")
@@ -118,8 +120,19 @@ def test_packed_fp32_instruction_mix_shows_no_contraction():
     if not (os.path.exists(obj) and os.path.exists(tool)):
         pytest.skip("needs the built render_kernel.o and cuobjdump")
     sass = subprocess.run([tool, "-sass", obj], capture_output=True, text=True, check=True).stdout
-    n_add, n_mul, n_fma = (sass.count(f" {op} ") for op in ("FADD2", "FMUL2", "FFMA2"))
-    assert n_add > 0 and n_add == n_mul and 2 * n_fma == 3 * n_mul, (n_add, n_mul, n_fma)
+    counts, name = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            counts[name] = [0, 0, 0]
+        elif name:
+            for i, op in enumerate(("FADD2", "FMUL2", "FFMA2")):
+                if f" {op} " in line:
+                    counts[name][i] += 1
+    kernels = {n: c for n, c in counts.items() if "trace_kernel" in n}
+    assert len(kernels) >= 6
+    for n, c in kernels.items():
+        assert tuple(c) == ((48, 48, 72) if "trace_kernel_rg" in n else (60, 60, 108)), (n, c)
 
 
 def test_new_entry_points_fail_cleanly_without_a_gpu(mm):
