@@ -274,6 +274,8 @@ class SharedHostFrame:
     def __init__(self, mm, name, nbytes, create, register=True):
         import mmap
         import numpy as np
+        if os.environ.get("MM_BENCH_NO_SHM"):                      # test hook for the fallback leg
+            raise OSError("shared host frame disabled by MM_BENCH_NO_SHM")
         self.path = os.path.join("/dev/shm", name)
         if create:
             with open(self.path, "wb") as f:
@@ -462,43 +464,74 @@ def run_ours(a):
         hf.close()
     else:
         port = os.environ.get("MASTER_PORT", "0")
-        shared = None
-        if rank == 0:
-            shared = SharedHostFrame(mm, f"mm_bench_frame_{port}", frame_bytes, create=True)
+        shared, shared_err = None, ""
+        try:
+            if rank == 0:
+                shared = SharedHostFrame(mm, f"mm_bench_frame_{port}", frame_bytes, create=True)
+        except Exception as e:
+            shared_err = f"{type(e).__name__}: {e}"
         barrier()
-        if rank != 0:
-            shared = SharedHostFrame(mm, f"mm_bench_frame_{port}", frame_bytes, create=False)
+        try:
+            if rank != 0:
+                shared = SharedHostFrame(mm, f"mm_bench_frame_{port}", frame_bytes, create=False)
+        except Exception as e:
+            shared_err = f"{type(e).__name__}: {e}"
+        ok_all = torch.tensor([1 if shared is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+        use_shared = int(ok_all.item()) == 1
+        if not use_shared and shared is not None:
+            shared.close(); shared = None
         mine = mm.Params.from_buffer_copy(bytes(frame.my))
         chunk_arr = np.ascontiguousarray(chunks)
-        if mine.group_count:
-            r.render_into(u, mine, chunk_arr.ctypes.data, len(chunk_arr), shared.ptr)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            u.time = 1000 + i
+        if use_shared:
             if mine.group_count:
-                c = r.render_into(u, mine, None, 0, shared.ptr)          # this rank's groups -> the one shared host frame
-                e2e_rays += c["rays"]
-            dist.barrier()
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
+                r.render_into(u, mine, chunk_arr.ctypes.data, len(chunk_arr), shared.ptr)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                u.time = 1000 + i
+                if mine.group_count:
+                    c = r.render_into(u, mine, None, 0, shared.ptr)          # this rank's groups -> the one shared host frame
+                    e2e_rays += c["rays"]
+                dist.barrier()
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
+            e2e_api = ("mm_render per rank (its interleaved groups) with out_rgba = ONE frame in shared pinned host memory (/dev/shm, "
+                       "mm_host_register in every rank): each kernel stores its pixels straight into it, N PCIe links in parallel; barrier")
+        else:
+            # no shared pinned frame on this box (e.g. /dev/shm not writable): device exchange, then rank 0 copies the assembled
+            # frame to its pinned memory (round 1's path)
+            host_frame = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+            r.set_stream(frame.stream.cuda_stream)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                u.time = 1000 + i
+                img = frame.render_frame(u)
+                if rank == 0:
+                    host_frame.copy_(img, non_blocking=True)
+                torch.cuda.synchronize()
+                e2e_rays += r.last_counters()["rays"] if frame.my.group_count else 0
+            barrier()
+            e2e_s = time.perf_counter() - t0
+            r.set_stream(None)
+            e2e_api = ("device exchange + assembled frame copied to rank 0's pinned host memory (shared pinned host frame unavailable: " + shared_err + ")")
         t = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device=dev)
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         e2e_s, e2e_rays = float(tmax[0].item()), int(t[1].item())
         d2h = frame_bytes + world * ctypes.sizeof(mm.Counters)
-        e2e_api = ("mm_render per rank (its interleaved groups) with out_rgba = ONE frame in shared pinned host memory (/dev/shm, "
-                   "mm_host_register in every rank): each kernel stores its pixels straight into it, N PCIe links in parallel; barrier")
         # parity of the host frame: one more frame at the parity time stamp
-        u.time = 4242
-        if mine.group_count:
-            r.render_into(u, mine, None, 0, shared.ptr)
-        barrier()
-        if rank == 0:
-            parity["shared_host_frame"] = sha(shared.array) == single_sha
-        barrier()
-        shared.close()
+        if use_shared:
+            u.time = 4242
+            if mine.group_count:
+                r.render_into(u, mine, None, 0, shared.ptr)
+            barrier()
+            if rank == 0:
+                parity["shared_host_frame"] = sha(shared.array) == single_sha
+            barrier()
+            shared.close()
 
     # ---- mm_multi: the same frame from ONE process over all N GPUs (rank 0 drives, the other ranks idle on the store) ------
     multi_info = None
