@@ -156,6 +156,18 @@ def test_rgba8_screen_mode_matches_oracle_and_blur_model(mm, oracle, noise, scen
         screen = np_oracle.present_blur(screen, rgba8=True)
         assert out.tobytes() == screen.tobytes()
         assert np.array_equal(out8, np.rint(screen * np.float32(255.0)).astype(np.uint8))
+    # the asynchronous form: one more frame, texels read back on the second stream into pinned memory
+    half.group_first, half.group_count = 0, (n + 1) // 2
+    u.time = 2
+    r.render(u, half, ch)
+    oracle.render(sc, noise, u, half, ch, out=screen)
+    hf = mm.HostFrame(H, W)                                   # pinned; its first H*W*4 bytes receive the texels
+    r.present_async_rgba8(hf.ptr)
+    r.wait_present()
+    screen = np_oracle.present_blur(screen, rgba8=True)
+    texels = np.frombuffer(hf.array.tobytes()[: H * W * 4], dtype=np.uint8).reshape(H, W, 4)
+    assert np.array_equal(texels, np.rint(screen * np.float32(255.0)).astype(np.uint8))
+    hf.close()
     r.close()
 
 
