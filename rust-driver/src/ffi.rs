@@ -55,6 +55,12 @@ extern "C" {
                            out_rgba: *mut f32, counters: *mut Counters) -> c_int;
     pub fn mm_multi_last_ms(m: *mut mm_multi, ms: *mut f32) -> c_int;
     pub fn mm_present(ctx: *mut mm_ctx, out_rgba: *mut f32) -> c_int;
+    // present_drawable + commit without wait (main.rs:893-894): blur now, read-back on a second stream
+    pub fn mm_present_async(ctx: *mut mm_ctx, out_rgba_pinned: *mut f32) -> c_int;
+    pub fn mm_present_async_rgba8(ctx: *mut mm_ctx, out_rgba8_pinned: *mut u8) -> c_int;
+    pub fn mm_wait_present(ctx: *mut mm_ctx) -> c_int;
+    pub fn mm_host_alloc(bytes: usize, out: *mut *mut std::ffi::c_void) -> c_int;
+    pub fn mm_host_free(ptr: *mut std::ffi::c_void) -> c_int;
     pub fn mm_last_ms(ctx: *mut mm_ctx, ms: *mut f32) -> c_int;
     pub fn mm_scene_build(maze_n: u32, seed: u64, fast_bvh: c_int, out: *mut *mut mm_scene) -> c_int;
     pub fn mm_scene_free(s: *mut mm_scene) -> c_int;
