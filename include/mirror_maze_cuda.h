@@ -304,6 +304,9 @@ int mm_microbench(mm_ctx *ctx, int kind, uint64_t table_bytes, double *result);
  * the fast sequence and __fdiv_rn, and returns how many differ (must be 0).
  */
 int mm_selftest_quotient(mm_ctx *ctx, uint64_t n_pairs, uint64_t seed, uint64_t *mismatches);
+/* The present blur divides by 3 (shaders.metal:222) with a three-operation exact sequence instead of the IEEE divide; this
+ * compares the two over ALL 2^32 float bit patterns and returns how many differ (must be 0). */
+int mm_selftest_div3(mm_ctx *ctx, uint64_t *mismatches);
 
 /*
  * Verification hook for the rect edge tests (reference src/shaders.metal:60-63: d = dot(rv, edge) / length(edge),

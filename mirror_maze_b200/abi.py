@@ -137,6 +137,7 @@ PROTOTYPES = {
     "mm_stream": (C.c_int, [_vp, _P(_vp)]),
     "mm_get_scene_info": (C.c_int, [_vp, _P(SceneInfo)]),
     "mm_selftest_quotient": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _P(C.c_uint64)]),
+    "mm_selftest_div3": (C.c_int, [_vp, _P(C.c_uint64)]),
     "mm_render_peers_device": (C.c_int, [_vp, _P(Uniform), _P(Params), _P(C.c_void_p), C.c_uint32]),
     "mm_rect_edge_thresholds": (C.c_int, [C.c_float, _P(C.c_float), _P(C.c_float)]),
     "mm_axis_rect": (C.c_int, [_P(Plane), _P(C.c_float), _P(C.c_uint32)]),

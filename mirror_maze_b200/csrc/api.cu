@@ -755,6 +755,19 @@ int mm_selftest_quotient(mm_ctx *ctx, uint64_t n_pairs, uint64_t seed, uint64_t 
     return MM_OK;
 }
 
+int mm_selftest_div3(mm_ctx *ctx, uint64_t *mismatches) {
+    if (!ctx || !mismatches) return MM_ERR_INVALID;
+    ctx->err.clear();
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->stream));
+    CK(launch_div3_selftest(&ctx->d_counters->paths, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *mismatches = ctx->h_counters->paths;
+    ctx->timed = false;
+    return MM_OK;
+}
+
 int mm_last_counters(mm_ctx *ctx, mm_counters *out) {
     if (!ctx || !out) return MM_ERR_INVALID;
     ctx->err.clear();

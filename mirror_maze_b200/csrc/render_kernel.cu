@@ -385,23 +385,52 @@ __global__ void quot_selftest_kernel(uint64_t n, uint64_t seed, unsigned long lo
 
 // fragment_shader's 5-tap blur (shaders.metal:214-225), ping-pong: one thread per pixel, one float4 per tap.  HBM-bound:
 // 16 B read + 16 B written per pixel (the four neighbour taps hit L1/L2).
+// x / 3 without the divide: q0 = RN(x * r), e = x - 3 q0 (exact by FMA), q = RN(q0 + e * r) with r = RN(1/3).  Equal to __fdiv_rn(x, 3)
+// for every float whose quotient is a normal number — established by exhaustion over all 2^32 bit patterns (div3_selftest_kernel,
+// mm_selftest_div3; tests/test_next_rows.py) — and guarded for the rest (tiny values take the IEEE divide).  x / 2 is x * 0.5: the
+// same real number, hence the same rounding.
+__device__ __forceinline__ float div3(float x) {
+    if (!(fabsf(x) >= 1e-30f && fabsf(x) <= 3.4028234663852886e38f)) return fdiv(x, 3.0f);   // zeros, denormal quotients, infinities, NaN: the literal divide
+    const float r = 0.3333333432674407958984375f;                          // RN(1/3)
+    const float q0 = fmul(x, r);
+    return __fmaf_rn(__fmaf_rn(-3.0f, q0, x), r, q0);
+}
+__global__ void div3_selftest_kernel(unsigned long long *mismatches) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (uint64_t i = tid; i < (1ull << 32); i += stride) {
+        const float x = __uint_as_float((uint32_t)i);
+        const float a = div3(x), b = fdiv(x, 3.0f);
+        if (__float_as_uint(a) != __float_as_uint(b) && !(a != a && b != b)) bad++;   // NaN payloads aside, bit for bit
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+// fragment_shader's 5-tap blur (shaders.metal:214-225), ping-pong.  HBM-bound: 16 B read + 16 B written per pixel (the four
+// neighbour taps hit L1/L2).  One thread handles two horizontally adjacent pixels (8 loads for 2 pixels instead of 10).
 __global__ void __launch_bounds__(256) blur_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, uint32_t W, uint32_t H, bool q8,
                                                    uchar4 *__restrict__ bytes) {
-    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= W || y >= H) return;
+    const uint32_t x0 = 2u * (blockIdx.x * blockDim.x + threadIdx.x), y = blockIdx.y;
+    if (x0 >= W || y >= H) return;
     const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     const size_t row = (size_t)y * W;
-    const float4 c = __ldg(src + row + x);
-    const float4 r = x + 1 < W ? __ldg(src + row + x + 1) : zero, l = x > 0 ? __ldg(src + row + x - 1) : zero;
-    const float4 d = y + 1 < H ? __ldg(src + row + W + x) : zero, u = y > 0 ? __ldg(src + row - W + x) : zero;
-    float4 o;
-    o.x = fdiv(fadd(fadd(c.x, fdiv(fadd(r.x, l.x), 2.0f)), fdiv(fadd(d.x, u.x), 2.0f)), 3.0f);
-    o.y = fdiv(fadd(fadd(c.y, fdiv(fadd(r.y, l.y), 2.0f)), fdiv(fadd(d.y, u.y), 2.0f)), 3.0f);
-    o.z = fdiv(fadd(fadd(c.z, fdiv(fadd(r.z, l.z), 2.0f)), fdiv(fadd(d.z, u.z), 2.0f)), 3.0f);
-    o.w = 1.0f;
-    if (q8) o = quant8(o);
-    dst[row + x] = o;
-    if (bytes) bytes[row + x] = make_uchar4((unsigned char)unorm8(o.x), (unsigned char)unorm8(o.y), (unsigned char)unorm8(o.z), (unsigned char)unorm8(o.w));
+    const bool two = x0 + 1 < W;
+    const float4 c0 = __ldg(src + row + x0), c1 = two ? __ldg(src + row + x0 + 1) : zero;
+    const float4 l0 = x0 > 0 ? __ldg(src + row + x0 - 1) : zero, r1 = x0 + 2 < W ? __ldg(src + row + x0 + 2) : zero;
+    const float4 d0 = y + 1 < H ? __ldg(src + row + W + x0) : zero, u0 = y > 0 ? __ldg(src + row - W + x0) : zero;
+    const float4 d1 = (two && y + 1 < H) ? __ldg(src + row + W + x0 + 1) : zero, u1 = (two && y > 0) ? __ldg(src + row - W + x0 + 1) : zero;
+    auto tap = [](float c, float r, float l, float d, float u) {             // :217-222, one channel
+        return div3(fadd(fadd(c, fmul(fadd(r, l), 0.5f)), fmul(fadd(d, u), 0.5f)));
+    };
+    float4 o0 = make_float4(tap(c0.x, c1.x, l0.x, d0.x, u0.x), tap(c0.y, c1.y, l0.y, d0.y, u0.y), tap(c0.z, c1.z, l0.z, d0.z, u0.z), 1.0f);
+    float4 o1 = make_float4(tap(c1.x, r1.x, c0.x, d1.x, u1.x), tap(c1.y, r1.y, c0.y, d1.y, u1.y), tap(c1.z, r1.z, c0.z, d1.z, u1.z), 1.0f);
+    if (q8) { o0 = quant8(o0); o1 = quant8(o1); }
+    dst[row + x0] = o0;
+    if (two) dst[row + x0 + 1] = o1;
+    if (bytes) {
+        bytes[row + x0] = make_uchar4((unsigned char)unorm8(o0.x), (unsigned char)unorm8(o0.y), (unsigned char)unorm8(o0.z), (unsigned char)unorm8(o0.w));
+        if (two) bytes[row + x0 + 1] = make_uchar4((unsigned char)unorm8(o1.x), (unsigned char)unorm8(o1.y), (unsigned char)unorm8(o1.z), (unsigned char)unorm8(o1.w));
+    }
 }
 
 // Micro-benchmarks for the two rooflines the path is measured against (SURVEY §8 d): how fast can this GPU fetch 56 useful
@@ -485,9 +514,14 @@ cudaError_t launch_scatter_all(const float *gathered, float *image, const mm_chu
 
 cudaError_t launch_blur(const float *src, float *dst, uint32_t W, uint32_t H, cudaStream_t stream, bool quant8, uint8_t *bytes) {
     if (W == 0 || H == 0) return cudaSuccess;
-    dim3 grid((W + 255) / 256, H);
+    dim3 grid((W + 511) / 512, H);                                            // two pixels per thread
     blur_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), W, H, quant8,
                                           reinterpret_cast<uchar4 *>(bytes));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_div3_selftest(unsigned long long *d_mismatches, cudaStream_t stream) {
+    div3_selftest_kernel<<<148 * 16, 256, 0, stream>>>(d_mismatches);
     return cudaGetLastError();
 }
 

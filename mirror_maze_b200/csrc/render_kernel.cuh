@@ -131,6 +131,7 @@ cudaError_t launch_mb_ffma(uint32_t iters, unsigned blocks, float *sink, cudaStr
 cudaError_t launch_scatter_all(const float *gathered, float *image, const mm_chunk *chunks, uint32_t world, uint32_t max_count,
                                uint32_t n_groups, uint32_t chunk, uint32_t W, uint32_t H, cudaStream_t stream);
 cudaError_t launch_blur(const float *src, float *dst, uint32_t W, uint32_t H, cudaStream_t stream, bool quant8 = false, uint8_t *bytes = nullptr);
+cudaError_t launch_div3_selftest(unsigned long long *d_mismatches, cudaStream_t stream);
 cudaError_t launch_quot_selftest(uint64_t n, uint64_t seed, unsigned long long *d_mismatches, cudaStream_t stream);
 cudaError_t launch_scatter(const float *tiles, float *image, const mm_chunk *chunks, uint32_t grid_groups, uint32_t group_first,
                            uint32_t group_step, uint32_t group_count, uint32_t chunk, uint32_t W, uint32_t H, cudaStream_t stream);

@@ -231,6 +231,12 @@ class Renderer:
         self._ck(self._lib.mm_selftest_quotient(self._ctx, n_pairs, seed, C.byref(bad)))
         return int(bad.value)
 
+    def selftest_div3(self):
+        """Mismatches between the blur's exact x / 3 sequence and __fdiv_rn(x, 3) over all 2^32 floats (must be 0)."""
+        bad = C.c_uint64()
+        self._ck(self._lib.mm_selftest_div3(self._ctx, C.byref(bad)))
+        return int(bad.value)
+
     def last_ms(self):
         ms = C.c_float()
         self._ck(self._lib.mm_last_ms(self._ctx, C.byref(ms)))
@@ -302,6 +308,12 @@ class MultiRenderer:
         p = C.c_void_p()
         self._ck(self._lib.mm_multi_frame_device(self._m, index, C.byref(p)))
         return p.value
+
+    def selftest_div3(self):
+        """Mismatches between the blur's exact x / 3 sequence and __fdiv_rn(x, 3) over all 2^32 floats (must be 0)."""
+        bad = C.c_uint64()
+        self._ck(self._lib.mm_selftest_div3(self._ctx, C.byref(bad)))
+        return int(bad.value)
 
     def last_ms(self):
         ms = C.c_float()

@@ -203,3 +203,9 @@ def test_present_async_delivers_the_frames_of_the_synchronous_present(mm, noise,
     ra.close(); rb.close()
     for fr in frames:
         fr.close()
+
+
+@pytest.mark.gpu
+def test_blur_divide_by_three_is_exact_for_every_float(renderer):
+    """blur_kernel's x / 3 (three FMA-pipe operations, guarded for tiny values) == __fdiv_rn(x, 3) on all 2^32 bit patterns."""
+    assert renderer.selftest_div3() == 0
